@@ -1,0 +1,121 @@
+/*
+ * mrscore.h — C-ABI of libmrscore.so: the B200-native drop-in for MusicRecommendation's scoring hot path.
+ *
+ * The reference (alberto-paparella/MusicRecommendation, Scala) has no FFI of its own; the boundary is the public method
+ * surface of `MusicRecommender` (reference file src/main/scala/music_recommandation/MusicRecommender.scala, "MR" below)
+ * and the per-partition objects of distributed.scala ("DIST").  Each entry point names the reference interface whose body
+ * it replaces.  Plain C: pointers and sizes only, so that JNI, JNA, Panama and ctypes all bind it directly
+ * (INTEGRATION.md shows the Scala/JNI stub).
+ *
+ * Conventions
+ *  - One handle = one GPU = one process-local scorer ("one process per GPU"); handles are not thread-safe, use one per
+ *    calling thread (Spark executor task threads, DIST:451-478).
+ *  - Users and songs are dense int32 ids assigned in ascending String.compareTo order, so int order == Ordering.String
+ *    (main.scala:57) and dense outputs are already in the order of the alignment sort main.scala:57-59.
+ *  - Every function returns MR_OK or an error code; mr_last_error() gives the message.  Nothing exits or throws across
+ *    the boundary (the reference calls System.exit(2) / System.exit(-1), MR:326, 366-369: the host wrapper maps
+ *    MR_ERR_KEY_MISMATCH -> exit(2) and MR_ERR_PARAM_RANGE -> stderr message + exit(-1)).
+ *  - Outputs are copied into caller-allocated host buffers; the library owns only device memory behind the handle.
+ *  - There is no CPU fallback: without a CUDA device mr_create fails with MR_ERR_CUDA.
+ */
+#ifndef MRSCORE_H
+#define MRSCORE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mr_handle mr_handle;
+
+enum {
+  MR_OK = 0,
+  MR_ERR_PARAM_RANGE = 1,   /* blend parameter outside [0,1]            (System.exit(-1), MR:366-369, 434-437) */
+  MR_ERR_KEY_MISMATCH = 2,  /* ubm / ibm arrays not aligned             (System.exit(2),  MR:326, 379, 445)    */
+  MR_ERR_CUDA = 3,
+  MR_ERR_NCCL = 4,
+  MR_ERR_OOM = 5,
+  MR_ERR_BAD_ARG = 6,
+  MR_ERR_STATE = 7          /* call order: nothing loaded, no test users, no top-k computed ... */
+};
+
+/* model selectors */
+enum {
+  MR_UBM = 0,    /* getUserBasedModel[P]                MR:132, 177; DIST UserBasedModel  DIST:172-239 */
+  MR_IBM = 1,    /* getItemBasedModel[P]                MR:222, 268; DIST ItemBasedModel  DIST:244-310 */
+  MR_LC = 2,     /* getLinearCombinationModel[P]        MR:317, 340   param = alpha                     */
+  MR_AGG = 3,    /* getAggregationModel[P]              MR:361, 396   param = itemBasedPercentage       */
+  MR_STOCH = 4   /* getStochasticCombinationModel[P]    MR:429, 461   param = itemBasedProbability, seed = java.util.Random seed */
+};
+
+/* mr_create flags */
+enum {
+  MR_ENGINE_AUTO = 0,     /* tensor-core count GEMM when the dense 0/1 operands fit in HBM, else inverted-index counts */
+  MR_ENGINE_TENSOR = 1,   /* force K1 = tcgen05 int8 GEMM */
+  MR_ENGINE_SPARSE = 2,   /* force K1s = inverted-index counts */
+  MR_ENGINE_MASK = 3,
+  MR_PROFILE = 4          /* record CUDA events around every kernel phase (mr_get_timing) */
+};
+
+/* Create a scorer on CUDA device device_ids[0] (n_devices must be 1: one process per GPU).  Replaces nothing in the
+ * reference; it is the native half of `new MusicRecommender(...)` (MR:12). */
+int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned flags);
+void mr_destroy(mr_handle* h);
+const char* mr_last_error(const mr_handle* h);
+
+/* Hand over the data model the constructor builds (MR:26-62): CSR of the binary train matrix (T x S) and of the visible
+ * half of the test users (U x S), column ids ascending and unique within a row, plus the `.length` values the cosine
+ * denominators use (MR:147: per-user song counts; MR:237: per-song listener counts over train AND test-visible rows).
+ * n_test may be 0 (train replica only; test users follow through mr_set_test_users). */
+int mr_load(mr_handle* h, int n_train, int n_test, int n_songs,
+            const int64_t* tr_rowptr, const int32_t* tr_col,
+            const int64_t* te_rowptr, const int32_t* te_col,
+            const int32_t* deg_train, const int32_t* deg_test, const int32_t* deg_song_all);
+
+/* Replace the current test users by a shard — the unit DIST's getRanks1(user) works on (DIST:198-205, 269-276), i.e.
+ * `ctx.parallelize(testUsers, slices)` (DIST:451).  pair_index_base = number of scored pairs of all test users that sort
+ * before this shard and n_pairs_total = ubm.length of the whole model; both only matter for MR_AGG / MR_STOCH (MR:372,
+ * 381, 447).  Pass n_pairs_total = 0 for "this shard is the whole test set". */
+int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const int32_t* te_col, const int32_t* deg_test,
+                      int64_t pair_index_base, int64_t n_pairs_total);
+
+/* Parity probes for kernel K1: out[u*T + v] = |I_u ∩ I_v| (numerator of MR:142-145), and rows [s0,s1) of the train
+ * co-occurrence matrix out[(i-s0)*S + j] = |U_i ∩ U_j| over train users (numerator of MR:232-235). */
+int mr_counts_ubm(mr_handle* h, int32_t* out_UxT);
+int mr_counts_ibm(mr_handle* h, int s0, int s1, int32_t* out_rows);
+
+/* Cosine similarities with the normalisation fused into the GEMM epilogue (fp32): user-user MR:140-149 and rows [s0,s1) of
+ * item-item MR:230-239 (denominator uses the train+test listener counts, MR:237). */
+int mr_similarity_ubm(mr_handle* h, float* out_UxT);
+int mr_similarity_ibm(mr_handle* h, int s0, int s1, float* out_rows);
+
+/* Whole model as the dense row-major U x S matrix of fp64 scores in main.scala:57-59 order; NaN marks the listened pairs
+ * the reference does not emit (MR:109).  model = MR_UBM | MR_IBM.  Small configurations only (U*S*8 bytes). */
+int mr_score_dense(mr_handle* h, int model, double* out_UxS);
+
+/* Blends on materialised, aligned model arrays (MR:317-481): kind = MR_LC | MR_AGG | MR_STOCH.  first_index / n_total as in
+ * mr_set_test_users (0 / 0 for whole models). */
+int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const double* ubm, const double* ibm, double* out,
+                   int64_t n_pairs, int64_t first_index, int64_t n_total);
+
+/* getTopK(model, k): per test user the k best unlistened songs, score descending then song id ascending (new derived
+ * output named by north_star; the reference has no ranking step).  out_song / out_score are U x k (song -1 / score 0.0 past
+ * out_len[u] = min(k, S - |I_u|)).  1 <= k <= 1024.  model = any MR_* selector; blends are fused into the select. */
+int mr_topk(mr_handle* h, int model, double param, uint64_t seed, int k, int32_t* out_song, double* out_score, int32_t* out_len);
+
+/* The same, split for callers that keep results on the device between steps: compute only (results stay in HBM), then fetch. */
+int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k);
+int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int32_t* out_len);
+
+/* Introspection used by bench.py / tests. */
+enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5, MR_T_N = 6 };
+int mr_get_timing(mr_handle* h, double* ms_out, int n);      /* accumulated CUDA-event ms per phase since the last reset */
+int mr_reset_timing(mr_handle* h);
+int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated] */
+void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRSCORE_H */

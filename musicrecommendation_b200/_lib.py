@@ -1,0 +1,63 @@
+"""ctypes binding of libmrscore.so (include/mrscore.h).  No fallback: a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SO = PKG / "libmrscore.so"
+
+MR_OK, MR_ERR_PARAM_RANGE, MR_ERR_KEY_MISMATCH, MR_ERR_CUDA, MR_ERR_NCCL, MR_ERR_OOM, MR_ERR_BAD_ARG, MR_ERR_STATE = range(8)
+MR_UBM, MR_IBM, MR_LC, MR_AGG, MR_STOCH = range(5)
+MR_ENGINE_AUTO, MR_ENGINE_TENSOR, MR_ENGINE_SPARSE = 0, 1, 2
+MR_PROFILE = 4
+TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other"]
+
+# every symbol include/mrscore.h declares
+SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_counts_ubm", "mr_counts_ibm",
+           "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_topk", "mr_topk_device",
+           "mr_topk_fetch", "mr_get_timing", "mr_reset_timing", "mr_get_info", "mr_stream"]
+
+_lib = None
+
+
+class MrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmrscore error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def load():
+    """dlopen libmrscore.so.  Raises if it has not been built — the product path never substitutes a CPU implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not SO.exists():
+        raise ImportError(f"{SO} is missing: build it with `python -m musicrecommendation_b200.build` (needs nvcc). "
+                          "There is no CPU fallback for the scoring path.")
+    lib = C.CDLL(str(SO))
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
+    lib.mr_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32, C.c_uint]
+    lib.mr_destroy.argtypes = [vp]
+    lib.mr_destroy.restype = None
+    lib.mr_last_error.argtypes = [vp]
+    lib.mr_last_error.restype = C.c_char_p
+    lib.mr_load.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.mr_set_test_users.argtypes = [vp, i32, vp, vp, vp, i64, i64]
+    lib.mr_counts_ubm.argtypes = [vp, vp]
+    lib.mr_counts_ibm.argtypes = [vp, i32, i32, vp]
+    lib.mr_similarity_ubm.argtypes = [vp, vp]
+    lib.mr_similarity_ibm.argtypes = [vp, i32, i32, vp]
+    lib.mr_score_dense.argtypes = [vp, i32, vp]
+    lib.mr_blend_dense.argtypes = [vp, i32, dbl, u64, vp, vp, vp, i64, i64, i64]
+    lib.mr_topk.argtypes = [vp, i32, dbl, u64, i32, vp, vp, vp]
+    lib.mr_topk_device.argtypes = [vp, i32, dbl, u64, i32]
+    lib.mr_topk_fetch.argtypes = [vp, i32, vp, vp, vp]
+    lib.mr_get_timing.argtypes = [vp, vp, i32]
+    lib.mr_reset_timing.argtypes = [vp]
+    lib.mr_get_info.argtypes = [vp, vp, i32]
+    lib.mr_stream.argtypes = [vp]
+    lib.mr_stream.restype = vp
+    _lib = lib
+    return lib

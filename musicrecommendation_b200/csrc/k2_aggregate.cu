@@ -1,0 +1,106 @@
+// k2_aggregate.cu — kernel K2: similarity-weighted score aggregation (HBM-bound gather).
+//
+// UBM  Sint[b][s] = sum_{v in U_s^train} Ct[v][b] * qv[v]              (MusicRecommender.scala:159-166: rank = sum of
+//                                                                     cosineSimilarity(user, u2) over train users who heard s)
+// IBM  Sint[b][s] = sum_{j in I_u, j != s} G[row(j)][s] * qd[j]        (MusicRecommender.scala:249-257)
+//
+// All accumulation is exact 64-bit integer arithmetic (canonical fixed point), so the result does not depend
+// on the summation order, on how a song's listeners are split across warps, or on how test users are sharded across GPUs.
+#include "mr_common.cuh"
+#include "mr_kernels.h"
+
+namespace mr {
+
+// One warp per work item (a song, or a <= kSplitLen slice of a popular song's listener list).  The 32 lanes hold the 128
+// test users of the batch, 4 per lane: every gathered row Ct[v][0..127] is one coalesced 256-byte read (8 bytes per lane).
+// Listener ids and their q factors are fetched 32 at a time (coalesced) and broadcast with shuffles.
+__global__ void __launch_bounds__(256)
+aggregate_ubm_kernel(AggItems items, const int* __restrict__ csc_idx, const uint32_t* __restrict__ qv,
+                     const uint16_t* __restrict__ ct, long long* __restrict__ sint, long long spitch) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const uint2* __restrict__ ct2 = reinterpret_cast<const uint2*>(ct);   // 4 x u16 per lane; row = 32 uint2
+  for (int it = blockIdx.x * warps_per_block + (threadIdx.x >> 5); it < items.n_items; it += gridDim.x * warps_per_block) {
+    const int song = items.song[it];
+    const long long beg = items.begin[it];
+    const int len = items.len[it];
+    unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int k = 0; k < len; k += 32) {
+      const int n = min(32, len - k);
+      int v = 0; uint32_t q = 0;
+      if (lane < n) { v = __ldg(csc_idx + beg + k + lane); q = __ldg(qv + v); }
+      int j = 0;
+      for (; j + 8 <= n; j += 8) {          // 8 independent 256 B row gathers in flight per warp
+        uint2 c[8]; uint32_t qq[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int vj = __shfl_sync(0xffffffffu, v, j + t);
+          qq[t] = __shfl_sync(0xffffffffu, q, j + t);
+          c[t] = __ldg(ct2 + static_cast<long long>(vj) * 32 + lane);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          a0 += static_cast<unsigned long long>(c[t].x & 0xffffu) * qq[t];
+          a1 += static_cast<unsigned long long>(c[t].x >> 16) * qq[t];
+          a2 += static_cast<unsigned long long>(c[t].y & 0xffffu) * qq[t];
+          a3 += static_cast<unsigned long long>(c[t].y >> 16) * qq[t];
+        }
+      }
+      for (; j < n; ++j) {
+        const int vj = __shfl_sync(0xffffffffu, v, j);
+        const uint32_t qj = __shfl_sync(0xffffffffu, q, j);
+        const uint2 c = __ldg(ct2 + static_cast<long long>(vj) * 32 + lane);
+        a0 += static_cast<unsigned long long>(c.x & 0xffffu) * qj;
+        a1 += static_cast<unsigned long long>(c.x >> 16) * qj;
+        a2 += static_cast<unsigned long long>(c.y & 0xffffu) * qj;
+        a3 += static_cast<unsigned long long>(c.y >> 16) * qj;
+      }
+    }
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sint) + static_cast<long long>(4 * lane) * spitch + song;
+    if (items.split[it]) {
+      atomicAdd(dst, a0); atomicAdd(dst + spitch, a1); atomicAdd(dst + 2 * spitch, a2); atomicAdd(dst + 3 * spitch, a3);
+    } else {
+      dst[0] = a0; dst[spitch] = a1; dst[2 * spitch] = a2; dst[3 * spitch] = a3;
+    }
+  }
+}
+
+int launch_aggregate_ubm(const AggItems& items, const int* csc_idx, const uint32_t* qv, const uint16_t* ct, long long* sint,
+                         long long spitch, int num_sms, cudaStream_t st) {
+  if (items.n_items <= 0) return 0;
+  const int threads = 256, wpb = threads / 32;
+  long long blocks = (static_cast<long long>(items.n_items) + wpb - 1) / wpb;
+  const long long cap = static_cast<long long>(num_sms) * 8;   // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  aggregate_ubm_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(items, csc_idx, qv, ct, sint, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// IBM: one thread per (user, song); the |I_u| Gram rows of the user are read coalesced along the song axis.
+__global__ void __launch_bounds__(256)
+aggregate_ibm_kernel(const long long* __restrict__ te_ptr, const int* __restrict__ te_col, const int* __restrict__ te_grow,
+                     const uint32_t* __restrict__ qd, int u0, const int32_t* __restrict__ g, long long ldg, int n_songs,
+                     long long* __restrict__ sint, long long spitch) {
+  const int b = blockIdx.y;
+  const long long beg = te_ptr[u0 + b], end = te_ptr[u0 + b + 1];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_songs; s += gridDim.x * blockDim.x) {
+    unsigned long long acc = 0;
+    for (long long i = beg; i < end; ++i) {
+      const int j = __ldg(te_col + i);
+      const int32_t cnt = __ldg(g + static_cast<long long>(__ldg(te_grow + i)) * ldg + s);
+      if (j != s) acc += static_cast<unsigned long long>(static_cast<uint32_t>(cnt)) * __ldg(qd + j);   // s2 != song, MR:252
+    }
+    sint[static_cast<long long>(b) * spitch + s] = static_cast<long long>(acc);
+  }
+}
+
+int launch_aggregate_ibm(const long long* te_ptr, const int* te_col, const int* te_grow, const uint32_t* qd, int u0, int n_users,
+                         const int32_t* g, long long ldg, int n_songs, long long* sint, long long spitch, cudaStream_t st) {
+  if (n_users <= 0 || n_songs <= 0) return 0;
+  int gx = (n_songs + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  aggregate_ibm_kernel<<<dim3(gx, n_users), 256, 0, st>>>(te_ptr, te_col, te_grow, qd, u0, g, ldg, n_songs, sint, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mr

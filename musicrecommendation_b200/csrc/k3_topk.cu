@@ -1,0 +1,338 @@
+// k3_topk.cu — kernel K3: fp64 score finalisation, model blends and the per-user top-k select.
+//
+// Score finalisation (canonical arithmetic):   ubm = (double)Sint_u * rsa[u],  ibm = (double)Sint_i * rsd[s]
+// Blends (MusicRecommender.scala, element i = index of (user, song) in the (user asc, song asc) order of main.scala:57-59):
+//   LinearCombination   rank1 * alpha + rank2 * (1 - alpha)                         MR:328   (rank1 = UBM, rank2 = IBM)
+//   Aggregation         i < (pct * N).toInt ? ibm : ubm                              MR:372, 381-382
+//   Stochastic          java.util.Random(seed): (i+1)-th nextFloat() < prob ? ibm : ubm   MR:439, 447 (sequential version)
+// Top-k (new derived output): per test user, unlistened songs ordered by score descending, then song id
+//   ascending; first min(k, S - |I_u|).
+// All fp64 products/sums use explicit round-to-nearest intrinsics so that no FMA contraction can change the bits.
+#include "mr_common.cuh"
+#include "mr_kernels.h"
+
+namespace mr {
+
+__device__ __forceinline__ double blend_score(int model, long long su, long long si, double rsu, double rds, double alpha,
+                                              double oma, bool pick_ibm) {
+  switch (model) {
+    case MODEL_UBM: return __dmul_rn(__ll2double_rn(su), rsu);
+    case MODEL_IBM: return __dmul_rn(__ll2double_rn(si), rds);
+    case MODEL_LC:
+      return __dadd_rn(__dmul_rn(__dmul_rn(__ll2double_rn(su), rsu), alpha), __dmul_rn(__dmul_rn(__ll2double_rn(si), rds), oma));
+    default: return pick_ibm ? __dmul_rn(__ll2double_rn(si), rds) : __dmul_rn(__ll2double_rn(su), rsu);
+  }
+}
+
+// ---------------------------------------------------------------- listened-pair sentinel (getModel's filter, MR:109)
+__global__ void mask_listened_kernel(const long long* __restrict__ te_ptr, const int* __restrict__ te_col, int u0, int n_users,
+                                     long long* sint_u, long long* sint_i, long long spitch) {
+  const int b = blockIdx.x;
+  if (b >= n_users) return;
+  const long long beg = te_ptr[u0 + b], end = te_ptr[u0 + b + 1];
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const int s = te_col[i];
+    if (sint_u) sint_u[static_cast<long long>(b) * spitch + s] = kListened;
+    if (sint_i) sint_i[static_cast<long long>(b) * spitch + s] = kListened;
+  }
+}
+
+int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
+                         long long spitch, cudaStream_t st) {
+  if (n_users <= 0) return 0;
+  mask_listened_kernel<<<n_users, 128, 0, st>>>(te_ptr, te_col, u0, n_users, sint_u, sint_i, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- dense fp64 model rows (small configs / parity probes)
+__global__ void dense_scores_kernel(int model, const long long* __restrict__ sint, long long spitch, int u0, int n_songs,
+                                    const double* __restrict__ rsa, const double* __restrict__ rsd, double* __restrict__ out) {
+  const int b = blockIdx.y;
+  const double rsu = rsa[u0 + b];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_songs; s += gridDim.x * blockDim.x) {
+    const long long v = sint[static_cast<long long>(b) * spitch + s];
+    double r;
+    if (v < 0) r = __longlong_as_double(0x7ff8000000000000LL);   // NaN marks a pair the reference does not emit
+    else r = model == MODEL_UBM ? __dmul_rn(__ll2double_rn(v), rsu) : __dmul_rn(__ll2double_rn(v), rsd[s]);
+    out[static_cast<long long>(b) * n_songs + s] = r;
+  }
+}
+
+int launch_dense_scores(int model, const long long* sint, long long spitch, int u0, int n_users, int n_songs, const double* rsa,
+                        const double* rsd, double* out, cudaStream_t st) {
+  if (n_users <= 0 || n_songs <= 0) return 0;
+  int gx = (n_songs + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  dense_scores_kernel<<<dim3(gx, n_users), 256, 0, st>>>(model, sint, spitch, u0, n_songs, rsa, rsd, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- java.util.Random (48-bit LCG) with O(log n) jump-ahead
+constexpr unsigned long long kLcgA = 0x5DEECE66DULL, kLcgC = 0xBULL, kLcgMask = (1ULL << 48) - 1;
+
+__host__ __device__ inline unsigned long long lcg_jump(unsigned long long state, unsigned long long n) {
+  unsigned long long acc_mul = 1, acc_add = 0, cur_mul = kLcgA, cur_add = kLcgC;
+  while (n) {
+    if (n & 1) { acc_mul = (acc_mul * cur_mul) & kLcgMask; acc_add = (acc_add * cur_mul + cur_add) & kLcgMask; }
+    cur_add = ((cur_mul + 1) * cur_add) & kLcgMask;
+    cur_mul = (cur_mul * cur_mul) & kLcgMask;
+    n >>= 1;
+  }
+  return (acc_mul * state + acc_add) & kLcgMask;
+}
+
+// Selection bit per (user, song): 1 -> take the IBM score, 0 -> UBM.  One thread per 64-song word.
+__global__ void select_bits_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const int* __restrict__ te_col, int u0,
+                                   int n_songs, uint64_t* __restrict__ sel, long long sel_pitch_words) {
+  const int b = blockIdx.y;
+  const int u = u0 + b;
+  const int n_words = (n_songs + 63) / 64;
+  const long long beg = te_ptr[u], end = te_ptr[u + 1];
+  const int* row = te_col + beg;
+  const int row_len = static_cast<int>(end - beg);
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+    const int s0 = w * 64;
+    int lo = 0, hi = row_len;                       // listened songs with id < s0
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (row[m] < s0) lo = m + 1; else hi = m; }
+    int p = lo;
+    long long idx = bp.pair_base[u] + s0 - p;        // index of the first unlistened song >= s0 in MAIN:57-59 order
+    unsigned long long state = 0;
+    if (bp.model == MODEL_STOCH) state = lcg_jump((bp.seed ^ kLcgA) & kLcgMask, static_cast<unsigned long long>(idx));
+    uint64_t bits = 0;
+    const int s_end = min(s0 + 64, n_songs);
+    for (int s = s0; s < s_end; ++s) {
+      if (p < row_len && row[p] == s) { ++p; continue; }   // listened: not in the model, consumes no index / no draw
+      bool pick;
+      if (bp.model == MODEL_AGG) {
+        pick = idx < bp.agg_threshold;
+      } else {
+        state = (state * kLcgA + kLcgC) & kLcgMask;
+        const float f = static_cast<float>(static_cast<int>(state >> 24)) / static_cast<float>(1 << 24);   // nextFloat()
+        pick = static_cast<double>(f) < bp.prob;
+      }
+      bits |= static_cast<uint64_t>(pick) << (s - s0);
+      ++idx;
+    }
+    sel[static_cast<long long>(b) * sel_pitch_words + w] = bits;
+  }
+}
+
+int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,
+                       uint64_t* sel, long long sel_pitch_words, cudaStream_t st) {
+  if (n_users <= 0 || n_songs <= 0) return 0;
+  const int n_words = (n_songs + 63) / 64;
+  int gx = (n_words + 127) / 128;
+  select_bits_kernel<<<dim3(gx, n_users), 128, 0, st>>>(bp, te_ptr, te_col, u0, n_songs, sel, sel_pitch_words);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- top-k: radix select on the composite key (score, ~song)
+constexpr int kTopkThreads = 512;
+constexpr int kTopkCap = 2048;   // candidate buffer (>= k); bitonic-sorted in shared memory
+
+struct KeyCtx {
+  int model; double rsu, alpha, oma;
+  const long long* su; const long long* si; const double* rsd; const uint64_t* sel;
+};
+
+// Returns false for listened pairs.  Scores are >= 0, so their IEEE bit patterns order like unsigned integers.
+__device__ __forceinline__ bool load_key(const KeyCtx& c, int s, unsigned long long& kb) {
+  long long a = 0, b = 0;
+  if (c.model != MODEL_IBM) { a = c.su[s]; if (a < 0) return false; }
+  if (c.model != MODEL_UBM) { b = c.si[s]; if (b < 0) return false; }
+  bool pick = false;
+  if (c.model >= MODEL_AGG) pick = (c.sel[s >> 6] >> (s & 63)) & 1ULL;
+  const double rds = c.model != MODEL_UBM ? c.rsd[s] : 0.0;
+  kb = static_cast<unsigned long long>(__double_as_longlong(blend_score(c.model, a, b, c.rsu, rds, c.alpha, c.oma, pick)));
+  return true;
+}
+
+// digit d (0 = most significant) of the 96-bit composite (kb : 64, ~song : 32), 8 bits each
+__device__ __forceinline__ uint32_t key_digit(unsigned long long kb, uint32_t inv_song, int d) {
+  return d < 8 ? static_cast<uint32_t>(kb >> (56 - 8 * d)) & 255u : (inv_song >> (24 - 8 * (d - 8))) & 255u;
+}
+// compare the first nd digits of (kb, inv) against the prefix: -1 below, 0 equal, +1 above
+__device__ __forceinline__ int prefix_cmp(unsigned long long kb, uint32_t inv, unsigned long long phi, uint32_t plo, int nd) {
+  if (nd == 0) return 0;
+  if (nd <= 8) {
+    const int sh = 64 - 8 * nd;
+    const unsigned long long a = kb >> sh, b = phi >> sh;
+    return a < b ? -1 : (a > b ? 1 : 0);
+  }
+  if (kb != phi) return kb < phi ? -1 : 1;
+  const int sh = 32 - 8 * (nd - 8);
+  const uint32_t a = sh == 32 ? 0u : inv >> sh, b = sh == 32 ? 0u : plo >> sh;
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long long* __restrict__ sint_i, long long spitch,
+            const uint64_t* __restrict__ sel, long long sel_pitch_words, int u0, int n_songs, const double* __restrict__ rsa,
+            const double* __restrict__ rsd, int k, int* __restrict__ out_song, double* __restrict__ out_score,
+            int* __restrict__ out_len) {
+  __shared__ unsigned long long s_key[kTopkCap];
+  __shared__ int s_song[kTopkCap];
+  __shared__ int s_hist[256];
+  __shared__ int s_count;
+  __shared__ int s_ctl[4];     // 0: chosen digit, 1: items strictly above the prefix bin, 2: bin count, 3: need
+
+  const int b = blockIdx.x;
+  const int u = u0 + b;
+  const int tid = threadIdx.x, lane = tid & 31;
+  KeyCtx c;
+  c.model = bp.model; c.rsu = rsa[u]; c.alpha = bp.alpha; c.oma = bp.one_minus_alpha;
+  c.su = sint_u ? sint_u + static_cast<long long>(b) * spitch : nullptr;
+  c.si = sint_i ? sint_i + static_cast<long long>(b) * spitch : nullptr;
+  c.rsd = rsd;
+  c.sel = sel ? sel + static_cast<long long>(b) * sel_pitch_words : nullptr;
+
+  unsigned long long phi = 0; uint32_t plo = 0;   // selected prefix digits
+  int nd = 0, above = 0, need = 0;
+  for (;;) {
+    for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < n_songs; s0 += kTopkThreads) {
+      const int s = s0 + tid;
+      unsigned long long kb = 0; bool ok = false;
+      if (s < n_songs) ok = load_key(c, s, kb);
+      const uint32_t inv = ~static_cast<uint32_t>(s);
+      ok = ok && prefix_cmp(kb, inv, phi, plo, nd) == 0;
+      const uint32_t dg = ok ? key_digit(kb, inv, nd) : 0xffffffffu;
+      // warp-aggregated histogram: peel the two most common digits of the warp with ballots, rest with plain atomics
+      uint32_t pending = __ballot_sync(0xffffffffu, ok);
+#pragma unroll 1
+      for (int round = 0; round < 2 && pending; ++round) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t ld = __shfl_sync(0xffffffffu, dg, leader);
+        const uint32_t same = __ballot_sync(0xffffffffu, dg == ld) & pending;
+        if (lane == leader) atomicAdd(&s_hist[ld], __popc(same));
+        pending &= ~same;
+      }
+      if ((pending >> lane) & 1u) atomicAdd(&s_hist[dg], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (nd == 0) {
+        int total = 0;
+        for (int i = 0; i < 256; ++i) total += s_hist[i];
+        s_ctl[3] = min(k, total);
+      }
+      const int want = s_ctl[3] - above;   // still needed from this prefix
+      int cum = 0, chosen = 0;
+      for (int d = 255; d >= 0; --d) {
+        if (cum + s_hist[d] >= want) { chosen = d; break; }
+        cum += s_hist[d];
+      }
+      s_ctl[0] = chosen; s_ctl[1] = above + cum; s_ctl[2] = s_hist[chosen];
+    }
+    __syncthreads();
+    need = s_ctl[3];
+    if (need == 0) break;
+    const int chosen = s_ctl[0];
+    above = s_ctl[1];
+    if (nd < 8) phi |= static_cast<unsigned long long>(chosen) << (56 - 8 * nd);
+    else plo |= static_cast<uint32_t>(chosen) << (24 - 8 * (nd - 8));
+    ++nd;
+    if (above + s_ctl[2] <= kTopkCap || nd == 12) break;
+    __syncthreads();
+  }
+
+  int* o_song = out_song + static_cast<long long>(u) * k;
+  double* o_score = out_score + static_cast<long long>(u) * k;
+  if (need == 0) {
+    for (int i = tid; i < k; i += kTopkThreads) { o_song[i] = -1; o_score[i] = 0.0; }
+    if (tid == 0) out_len[u] = 0;
+    return;
+  }
+
+  // collect every key whose first nd digits are >= the prefix (count = above + bin <= kTopkCap)
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < n_songs; s0 += kTopkThreads) {
+    const int s = s0 + tid;
+    unsigned long long kb = 0; bool ok = false;
+    if (s < n_songs) ok = load_key(c, s, kb);
+    ok = ok && prefix_cmp(kb, ~static_cast<uint32_t>(s), phi, plo, nd) >= 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ok) {
+        const int pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
+      }
+    }
+  }
+  __syncthreads();
+  const int n_cand = min(s_count, kTopkCap);
+  int n_sort = 1;
+  while (n_sort < n_cand) n_sort <<= 1;
+  for (int i = n_cand + tid; i < n_sort; i += kTopkThreads) { s_key[i] = 0; s_song[i] = 0x7fffffff; }   // sorts last
+  __syncthreads();
+  // bitonic sort, "better first": key descending, then song ascending
+  for (int size = 2; size <= n_sort; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n_sort / 2; i += kTopkThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc_block = (lo & size) == 0;   // first-half blocks keep the better element at the lower index
+        const unsigned long long ka = s_key[lo], kb2 = s_key[hi];
+        const int sa = s_song[lo], sb = s_song[hi];
+        const bool a_better = ka > kb2 || (ka == kb2 && sa < sb);
+        if (a_better != desc_block) { s_key[lo] = kb2; s_key[hi] = ka; s_song[lo] = sb; s_song[hi] = sa; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += kTopkThreads) {
+    if (i < need) { o_song[i] = s_song[i]; o_score[i] = __longlong_as_double(static_cast<long long>(s_key[i])); }
+    else { o_song[i] = -1; o_score[i] = 0.0; }
+  }
+  if (tid == 0) out_len[u] = need;
+}
+
+int launch_topk(const BlendParams& bp, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
+                long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
+                int* out_song, double* out_score, int* out_len, cudaStream_t st) {
+  if (n_users <= 0) return 0;
+  if (k <= 0 || k > kTopkCap / 2) return -2;
+  topk_kernel<<<n_users, kTopkThreads, 0, st>>>(bp, sint_u, sint_i, spitch, sel, sel_pitch_words, u0, n_songs, rsa, rsd, k,
+                                                out_song, out_score, out_len);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- blends on materialised model arrays (MR:317-481)
+__global__ void blend_arrays_kernel(BlendParams bp, const double* __restrict__ ubm, const double* __restrict__ ibm,
+                                    double* __restrict__ out, long long n, long long first_index) {
+  // each thread owns a contiguous chunk so the sequential Random stream is replayed with one jump per chunk
+  const long long n_threads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long chunk = (n + n_threads - 1) / n_threads;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long lo = t * chunk, hi = min(n, lo + chunk);
+  if (lo >= hi) return;
+  unsigned long long state = 0;
+  if (bp.model == MODEL_STOCH) state = lcg_jump((bp.seed ^ kLcgA) & kLcgMask, static_cast<unsigned long long>(first_index + lo));
+  for (long long i = lo; i < hi; ++i) {
+    double r;
+    if (bp.model == MODEL_LC) {
+      r = __dadd_rn(__dmul_rn(ubm[i], bp.alpha), __dmul_rn(ibm[i], bp.one_minus_alpha));
+    } else if (bp.model == MODEL_AGG) {
+      r = (first_index + i < bp.agg_threshold) ? ibm[i] : ubm[i];
+    } else {
+      state = (state * kLcgA + kLcgC) & kLcgMask;
+      const float f = static_cast<float>(static_cast<int>(state >> 24)) / static_cast<float>(1 << 24);
+      r = (static_cast<double>(f) < bp.prob) ? ibm[i] : ubm[i];
+    }
+    out[i] = r;
+  }
+}
+
+int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n,
+                        long long first_index, cudaStream_t st) {
+  if (n <= 0) return 0;
+  blend_arrays_kernel<<<148 * 4, 256, 0, st>>>(bp, ubm, ibm, out, n, first_index);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mr

@@ -1,0 +1,59 @@
+// mr_kernels.h — launcher prototypes shared between the kernel translation units and the C-ABI (mrscore.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mr {
+
+constexpr int kUserBatch = 128;   // test users per batch = UMMA M = 4 users per lane in the K2 gather
+
+enum { EPI_I32 = 0, EPI_U16_T = 1, EPI_COS_F32 = 2 };
+enum { MODEL_UBM = 0, MODEL_IBM = 1, MODEL_LC = 2, MODEL_AGG = 3, MODEL_STOCH = 4 };
+
+// ---- K1 (k1_count_gemm.cu)
+int launch_count_gemm(const uint8_t* A, long long a_rows, const uint8_t* B, long long b_rows, long long pitch, int M, int N,
+                      int epi, void* out, long long ld, const float* rsa, const float* rsb, int num_sms, cudaStream_t st);
+int launch_expand_rows(const long long* ptr, const int* idx, const int* rows, int row0, int n_rows, int n_rows_pad,
+                       long long pitch, uint8_t* out, cudaStream_t st);
+
+// ---- K1s (k1_sparse_count.cu): the same counts from the inverted index, for shapes whose dense operands do not fit
+int launch_sparse_count_u16t(const long long* te_ptr, const int* te_col, int u0, int n_users, const long long* csc_ptr,
+                             const int* csc_idx, uint16_t* ct, long long n_train, cudaStream_t st);
+int launch_sparse_gram_rows(const int* rows, int n_rows, const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr,
+                            const int* tr_col, int32_t* g, long long ldg, cudaStream_t st);
+
+// ---- K2 (k2_aggregate.cu)
+struct AggItems {            // work list over the train inverted index: one warp per item
+  const int* song;           // [n_items]
+  const long long* begin;    // [n_items] offset into csc_idx
+  const int* len;            // [n_items]
+  const uint8_t* split;      // [n_items] 1 -> the song is covered by several items (accumulate atomically)
+  int n_items;
+};
+int launch_aggregate_ubm(const AggItems& items, const int* csc_idx, const uint32_t* qv, const uint16_t* ct, long long* sint,
+                         long long spitch, int num_sms, cudaStream_t st);
+int launch_aggregate_ibm(const long long* te_ptr, const int* te_col, const int* te_grow, const uint32_t* qd, int u0, int n_users,
+                         const int32_t* g, long long ldg, int n_songs, long long* sint, long long spitch, cudaStream_t st);
+
+// ---- K3 (k3_topk.cu)
+int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
+                         long long spitch, cudaStream_t st);
+int launch_dense_scores(int model, const long long* sint, long long spitch, int u0, int n_users, int n_songs, const double* rsa,
+                        const double* rsd, double* out, cudaStream_t st);
+struct BlendParams {
+  int model;                 // MODEL_*
+  double alpha, one_minus_alpha;   // LC (MusicRecommender.scala:328)
+  long long agg_threshold;   // AGG: (pct * N).toInt (MR:372)
+  double prob;               // STOCH (MR:447)
+  unsigned long long seed;   // STOCH: java.util.Random seed
+  const long long* pair_base;  // [U+1] exclusive prefix of per-user scored-pair counts (index in MAIN:57-59 order)
+};
+int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,
+                       uint64_t* sel, long long sel_pitch_words, cudaStream_t st);
+int launch_topk(const BlendParams& bp, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
+                long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
+                int* out_song, double* out_score, int* out_len, cudaStream_t st);
+int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n, long long first_index,
+                        cudaStream_t st);
+
+}  // namespace mr

@@ -1,0 +1,682 @@
+// mrscore.cu — the C-ABI of include/mrscore.h: handle, data residency in HBM, and the batch pipeline K1 -> K2 -> K3.
+//
+// HBM layout:
+//   train CSR  (user -> songs)   tr_ptr i64[T+1], tr_col i32[nnz]        MusicRecommender.scala:55  trainUsersToSongsMap
+//   train CSC  (song -> users)   csc_ptr i64[S+1], csc_idx i32[nnz]      MusicRecommender.scala:60  songsToUsersMap (train part)
+//   qv u32[T], qd u32[S]         rint(2^31 / sqrt(deg))                   cosine denominators MR:147 / MR:237 in fixed point
+//   rsa f64[U], rsd f64[S]       2^-31 / sqrt(deg)                        the other half of each denominator
+//   A_tr  u8[T][pitchS], A_trT u8[S][pitchT]   dense 0/1 operands of the tensor-core count GEMM (tensor engine only)
+//   per batch of 128 test users: Ct u16[T][128], Sint_u / Sint_i i64[128][spitch], G i32[rows][ldg], select bits
+#include "../../include/mrscore.h"
+#include "mr_common.cuh"
+#include "mr_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mr;
+
+namespace {
+
+constexpr int kSplitLen = 4096;   // listeners per K2 work item
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+};
+
+}  // namespace
+
+struct mr_handle {
+  int device = 0; int num_sms = 148; unsigned flags = 0; int engine = MR_ENGINE_AUTO;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0; size_t dev_bytes = 0;
+  std::vector<void*> allocs;          // everything freed in mr_destroy
+  // train
+  int T = 0, S = 0; long long nnz_tr = 0; bool loaded = false;
+  long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
+  uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr;
+  std::vector<int32_t> deg_song;
+  int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
+  long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
+  uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
+  // test shard (freed / reallocated by mr_set_test_users)
+  int U = 0; long long nnz_te = 0; bool have_test = false;
+  std::vector<void*> test_allocs;
+  long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
+  std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
+  std::vector<long long> batch_row_off; int* d_rows = nullptr; int max_batch_rows = 0;
+  long long pair_index_base = 0, n_pairs_total = 0;
+  // workspaces
+  uint8_t *d_Ate = nullptr, *d_Aj = nullptr; uint16_t* d_ct = nullptr; long long *d_sint_u = nullptr, *d_sint_i = nullptr;
+  uint64_t* d_sel = nullptr; long long sel_pitch = 0; int32_t* d_g = nullptr; size_t g_bytes = 0; size_t aj_bytes = 0;
+  double* d_dense = nullptr; int32_t* d_cnt = nullptr; float* d_simf = nullptr;
+  // results
+  int *d_out_song = nullptr, *d_out_len = nullptr; double* d_out_score = nullptr; int out_k = 0; bool have_topk = false;
+  // profiling
+  cudaEvent_t ev[2] = {nullptr, nullptr}; double t_ms[MR_T_N] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(mr_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define MR_CUDA(h, expr)                                                                                       \
+  do {                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                  \
+    if (e__ != cudaSuccess)                                                                                    \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? MR_ERR_OOM : MR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                                \
+  } while (0)
+
+#define MR_LAUNCH(h, expr)                                                                     \
+  do {                                                                                         \
+    int rc__ = (expr);                                                                         \
+    (h)->launches++;                                                                           \
+    if (rc__ != 0) {                                                                           \
+      cudaError_t e__ = cudaGetLastError();                                                    \
+      return fail(h, MR_ERR_CUDA, "%s failed: rc=%d (%s)", #expr, rc__, cudaGetErrorString(e__)); \
+    }                                                                                          \
+  } while (0)
+
+template <class Tp>
+int dev_alloc(mr_handle* h, Tp** out, size_t count, std::vector<void*>& owner) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+  MR_CUDA(h, cudaMalloc(&p, bytes));
+  owner.push_back(p);
+  h->dev_bytes += bytes;
+  *out = static_cast<Tp*>(p);
+  return MR_OK;
+}
+
+template <class Tp>
+int dev_upload(mr_handle* h, Tp** out, const Tp* src, size_t count, std::vector<void*>& owner) {
+  int rc = dev_alloc(h, out, count, owner);
+  if (rc) return rc;
+  if (count) MR_CUDA(h, cudaMemcpyAsync(*out, src, count * sizeof(Tp), cudaMemcpyHostToDevice, h->stream));
+  return MR_OK;
+}
+
+inline uint32_t q_of(int32_t deg) { return deg <= 0 ? 0u : static_cast<uint32_t>(llrint(kQScale / std::sqrt(static_cast<double>(deg)))); }
+inline double rs_of(int32_t deg) { return deg <= 0 ? 0.0 : kQInv / std::sqrt(static_cast<double>(deg)); }
+inline float rsf_of(int32_t deg) { return deg <= 0 ? 0.0f : static_cast<float>(1.0 / std::sqrt(static_cast<double>(deg))); }
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+int check_csr(mr_handle* h, const char* what, int n_rows, int n_cols, const int64_t* ptr, const int32_t* col) {
+  if (!ptr || (!col && ptr[n_rows] > 0)) return fail(h, MR_ERR_BAD_ARG, "%s: null CSR arrays", what);
+  if (ptr[0] != 0) return fail(h, MR_ERR_BAD_ARG, "%s: rowptr[0] != 0", what);
+  for (int r = 0; r < n_rows; ++r) {
+    if (ptr[r + 1] < ptr[r]) return fail(h, MR_ERR_BAD_ARG, "%s: rowptr not monotone at row %d", what, r);
+    for (int64_t i = ptr[r]; i < ptr[r + 1]; ++i) {
+      if (col[i] < 0 || col[i] >= n_cols) return fail(h, MR_ERR_BAD_ARG, "%s: column id %d out of range at row %d", what, col[i], r);
+      if (i > ptr[r] && col[i] <= col[i - 1]) return fail(h, MR_ERR_BAD_ARG, "%s: row %d not ascending/unique", what, r);
+    }
+  }
+  return MR_OK;
+}
+
+struct PhaseTimer {   // CUDA events on the library stream around one phase (only with MR_PROFILE)
+  mr_handle* h; int phase; bool on;
+  PhaseTimer(mr_handle* hh, int ph) : h(hh), phase(ph), on((hh->flags & MR_PROFILE) != 0) {
+    if (on) cudaEventRecord(h->ev[0], h->stream);
+  }
+  ~PhaseTimer() {
+    if (!on) return;
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->t_ms[phase] += ms;
+  }
+};
+
+__global__ void ct_to_i32_kernel(const uint16_t* __restrict__ ct, int n_train, int nb, int32_t* __restrict__ out) {
+  // out[b][v] = Ct[v][b]
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(nb) * n_train;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / n_train), v = static_cast<int>(i % n_train);
+    out[i] = ct[static_cast<long long>(v) * kUserBatch + b];
+  }
+}
+__global__ void ct_to_cos_kernel(const uint16_t* __restrict__ ct, int n_train, int nb, const float* __restrict__ rsa,
+                                 const float* __restrict__ rsv, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(nb) * n_train;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / n_train), v = static_cast<int>(i % n_train);
+    out[i] = static_cast<float>(ct[static_cast<long long>(v) * kUserBatch + b]) * (rsa[b] * rsv[v]);
+  }
+}
+__global__ void gram_to_cos_kernel(const int32_t* __restrict__ g, long long ldg, const int* __restrict__ rows, int n_rows, int n_songs,
+                                   const float* __restrict__ rsd, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(n_rows) * n_songs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n_songs), s = static_cast<int>(i % n_songs);
+    out[i] = static_cast<float>(g[r * ldg + s]) * (rsd[rows[r]] * rsd[s]);
+  }
+}
+__global__ void iota_kernel(int* p, int start, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = start + i;
+}
+
+void free_list(std::vector<void*>& v) {
+  for (void* p : v) cudaFree(p);
+  v.clear();
+}
+
+// ---- K1 for one batch of test users -> Ct u16[T][128]
+int count_ubm_batch(mr_handle* h, int b0, int nb) {
+  if (h->engine == MR_ENGINE_TENSOR) {
+    {
+      PhaseTimer t(h, MR_T_EXPAND);
+      MR_LAUNCH(h, launch_expand_rows(h->d_te_ptr, h->d_te_col, nullptr, b0, nb, kUserBatch, h->pitchS, h->d_Ate, h->stream));
+    }
+    PhaseTimer t(h, MR_T_COUNT);
+    MR_LAUNCH(h, launch_count_gemm(h->d_Ate, kUserBatch, h->d_Atr, h->T, h->pitchS, kUserBatch, h->T, EPI_U16_T, h->d_ct, kUserBatch,
+                                   nullptr, nullptr, h->num_sms, h->stream));
+  } else {
+    PhaseTimer t(h, MR_T_COUNT);
+    MR_LAUNCH(h, launch_sparse_count_u16t(h->d_te_ptr, h->d_te_col, b0, nb, h->d_csc_ptr, h->d_csc_idx, h->d_ct, h->T, h->stream));
+  }
+  return MR_OK;
+}
+
+// ---- K1 for a list of Gram rows (device array of song ids) -> G i32[n_rows][ldg]
+int gram_rows(mr_handle* h, const int* d_rows, int n_rows) {
+  if (h->engine == MR_ENGINE_TENSOR) {
+    const int rows_pad = static_cast<int>(round_up(n_rows, 128));
+    {
+      PhaseTimer t(h, MR_T_EXPAND);
+      MR_LAUNCH(h, launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, d_rows, 0, n_rows, rows_pad, h->pitchT, h->d_Aj, h->stream));
+    }
+    PhaseTimer t(h, MR_T_COUNT);
+    MR_LAUNCH(h, launch_count_gemm(h->d_Aj, rows_pad, h->d_AtrT, h->S, h->pitchT, n_rows, h->S, EPI_I32, h->d_g, h->ldg, nullptr,
+                                   nullptr, h->num_sms, h->stream));
+  } else {
+    PhaseTimer t(h, MR_T_COUNT);
+    for (int r0 = 0; r0 < n_rows; r0 += 32768) {
+      const int n = std::min(32768, n_rows - r0);
+      MR_LAUNCH(h, launch_sparse_gram_rows(d_rows + r0, n, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                           h->d_g + static_cast<long long>(r0) * h->ldg, h->ldg, h->stream));
+    }
+  }
+  return MR_OK;
+}
+
+int ensure_gram_ws(mr_handle* h, int n_rows) {
+  const size_t need_g = static_cast<size_t>(round_up(std::max(n_rows, 1), 128)) * h->ldg * sizeof(int32_t);
+  if (need_g > h->g_bytes) {
+    int32_t* p; int rc = dev_alloc(h, &p, need_g / sizeof(int32_t), h->allocs);
+    if (rc) return rc;
+    h->d_g = p; h->g_bytes = need_g;
+  }
+  if (h->engine == MR_ENGINE_TENSOR) {
+    const size_t need_a = static_cast<size_t>(round_up(std::max(n_rows, 1), 128)) * h->pitchT;
+    if (need_a > h->aj_bytes) {
+      uint8_t* p; int rc = dev_alloc(h, &p, need_a, h->allocs);
+      if (rc) return rc;
+      h->d_Aj = p; h->aj_bytes = need_a;
+    }
+  }
+  return MR_OK;
+}
+
+enum RunMode { RUN_TOPK, RUN_DENSE, RUN_COUNTS_UBM, RUN_SIM_UBM };
+
+int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode mode, void* host_out) {
+  const bool need_ubm = model != MODEL_IBM;
+  const bool need_ibm = model != MODEL_UBM && mode != RUN_COUNTS_UBM && mode != RUN_SIM_UBM;
+  for (int b0 = 0; b0 < h->U; b0 += kUserBatch) {
+    const int nb = std::min(kUserBatch, h->U - b0);
+    if (need_ubm) {
+      int rc = count_ubm_batch(h, b0, nb);
+      if (rc) return rc;
+      if (mode == RUN_COUNTS_UBM || mode == RUN_SIM_UBM) {
+        PhaseTimer t(h, MR_T_OTHER);
+        if (mode == RUN_COUNTS_UBM) {
+          ct_to_i32_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->d_ct, h->T, nb, h->d_cnt);
+          h->launches++;
+          MR_CUDA(h, cudaMemcpyAsync(static_cast<int32_t*>(host_out) + static_cast<long long>(b0) * h->T, h->d_cnt,
+                                     static_cast<size_t>(nb) * h->T * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        } else {
+          ct_to_cos_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->d_ct, h->T, nb, h->d_rsa_f + b0, h->d_rsv_f, h->d_simf);
+          h->launches++;
+          MR_CUDA(h, cudaMemcpyAsync(static_cast<float*>(host_out) + static_cast<long long>(b0) * h->T, h->d_simf,
+                                     static_cast<size_t>(nb) * h->T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        }
+        MR_CUDA(h, cudaStreamSynchronize(h->stream));
+        continue;
+      }
+      PhaseTimer t(h, MR_T_AGG_UBM);
+      MR_CUDA(h, cudaMemsetAsync(h->d_sint_u, 0, static_cast<size_t>(kUserBatch) * h->spitch * sizeof(long long), h->stream));
+      AggItems items{h->d_item_song, h->d_item_begin, h->d_item_len, h->d_item_split, h->n_items};
+      MR_LAUNCH(h, launch_aggregate_ubm(items, h->d_csc_idx, h->d_qv, h->d_ct, h->d_sint_u, h->spitch, h->num_sms, h->stream));
+    }
+    if (need_ibm) {
+      const int batch = b0 / kUserBatch;
+      const long long r_off = h->batch_row_off[batch];
+      const int n_rows = static_cast<int>(h->batch_row_off[batch + 1] - r_off);
+      if (n_rows > 0) {
+        int rc = gram_rows(h, h->d_rows + r_off, n_rows);
+        if (rc) return rc;
+      }
+      PhaseTimer t(h, MR_T_AGG_IBM);
+      MR_LAUNCH(h, launch_aggregate_ibm(h->d_te_ptr, h->d_te_col, h->d_te_grow, h->d_qd, b0, nb, h->d_g, h->ldg, h->S, h->d_sint_i,
+                                        h->spitch, h->stream));
+    }
+    PhaseTimer t(h, MR_T_TOPK);
+    MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_col, b0, nb, need_ubm ? h->d_sint_u : nullptr,
+                                      need_ibm ? h->d_sint_i : nullptr, h->spitch, h->stream));
+    if (mode == RUN_DENSE) {
+      MR_LAUNCH(h, launch_dense_scores(model, need_ubm ? h->d_sint_u : h->d_sint_i, h->spitch, b0, nb, h->S, h->d_rsa, h->d_rsd,
+                                       h->d_dense, h->stream));
+      MR_CUDA(h, cudaMemcpyAsync(static_cast<double*>(host_out) + static_cast<long long>(b0) * h->S, h->d_dense,
+                                 static_cast<size_t>(nb) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      MR_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else {
+      if (model == MODEL_AGG || model == MODEL_STOCH)
+        MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, b0, nb, h->S, h->d_sel, h->sel_pitch, h->stream));
+      MR_LAUNCH(h, launch_topk(bp, need_ubm ? h->d_sint_u : nullptr, need_ibm ? h->d_sint_i : nullptr, h->spitch,
+                               (model == MODEL_AGG || model == MODEL_STOCH) ? h->d_sel : nullptr, h->sel_pitch, b0, nb, h->S, h->d_rsa,
+                               h->d_rsd, k, h->d_out_song, h->d_out_score, h->d_out_len, h->stream));
+    }
+  }
+  return MR_OK;
+}
+
+int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long long n_total, BlendParams* bp) {
+  memset(bp, 0, sizeof *bp);
+  bp->model = model;
+  if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
+  if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
+  if (model == MR_AGG) {
+    if (param < 0 || param > 1) return fail(h, MR_ERR_PARAM_RANGE, "Percentage must be between 0 and 1");   // MR:366-369
+    bp->agg_threshold = static_cast<long long>(param * static_cast<double>(n_total));                        // MR:372 .toInt
+  }
+  if (model == MR_STOCH) {
+    if (param < 0 || param > 1) return fail(h, MR_ERR_PARAM_RANGE, "Probability must be between 0 and 1");   // MR:434-437
+    bp->prob = param; bp->seed = seed;
+  }
+  return MR_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned flags) {
+  if (!out) return MR_ERR_BAD_ARG;
+  *out = nullptr;
+  mr_handle* h = new mr_handle();
+  *out = h;   // returned even on failure so that mr_last_error works; caller still calls mr_destroy
+  if (n_devices != 1 || !device_ids) return fail(h, MR_ERR_BAD_ARG, "n_devices must be 1 (one process per GPU), got %d", n_devices);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(h, MR_ERR_CUDA, "no CUDA device: %s — libmrscore has no CPU fallback", cudaGetErrorString(e));
+  h->device = device_ids[0];
+  if (h->device < 0 || h->device >= count) return fail(h, MR_ERR_BAD_ARG, "device id %d out of range (%d devices)", h->device, count);
+  MR_CUDA(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  MR_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) return fail(h, MR_ERR_CUDA, "device %d is sm_%d%d; libmrscore is built for sm_100a only", h->device, prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  h->flags = flags;
+  h->engine = flags & MR_ENGINE_MASK;
+  MR_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  MR_CUDA(h, cudaEventCreate(&h->ev[0]));
+  MR_CUDA(h, cudaEventCreate(&h->ev[1]));
+  return MR_OK;
+}
+
+void mr_destroy(mr_handle* h) {
+  if (!h) return;
+  if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+  free_list(h->test_allocs);
+  free_list(h->allocs);
+  if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+  if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* mr_last_error(const mr_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* tr_rowptr, const int32_t* tr_col,
+            const int64_t* te_rowptr, const int32_t* te_col, const int32_t* deg_train, const int32_t* deg_test,
+            const int32_t* deg_song_all) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (h->loaded) return fail(h, MR_ERR_STATE, "mr_load called twice on one handle");
+  if (n_train <= 0 || n_songs <= 0 || n_test < 0 || !deg_train || !deg_song_all) return fail(h, MR_ERR_BAD_ARG, "bad sizes / null degree arrays");
+  int rc = check_csr(h, "train", n_train, n_songs, tr_rowptr, tr_col);
+  if (rc) return rc;
+  MR_CUDA(h, cudaSetDevice(h->device));
+  const int T = n_train, S = n_songs;
+  const long long nnz = tr_rowptr[T];
+  h->T = T; h->S = S; h->nnz_tr = nnz;
+  h->pitchS = round_up(S, 128); h->pitchT = round_up(T, 128);
+  h->spitch = round_up(S, 32); h->ldg = round_up(S, 32);
+  h->deg_song.assign(deg_song_all, deg_song_all + S);
+
+  // inverted index (counting sort; listeners of a song ascending because rows are visited in order)
+  std::vector<long long> csc_ptr(static_cast<size_t>(S) + 1, 0);
+  for (long long i = 0; i < nnz; ++i) csc_ptr[tr_col[i] + 1]++;
+  for (int s = 0; s < S; ++s) csc_ptr[s + 1] += csc_ptr[s];
+  std::vector<int> csc_idx(static_cast<size_t>(std::max<long long>(nnz, 1)));
+  {
+    std::vector<long long> fill(csc_ptr.begin(), csc_ptr.end() - 1);
+    for (int v = 0; v < T; ++v)
+      for (long long i = tr_rowptr[v]; i < tr_rowptr[v + 1]; ++i) csc_idx[fill[tr_col[i]]++] = v;
+  }
+  // fixed-point cosine factors
+  std::vector<uint32_t> qv(T), qd(S);
+  std::vector<double> rsd(S);
+  std::vector<float> rsvf(T), rsdf(S);
+  for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v]); rsvf[v] = rsf_of(deg_train[v]); }
+  for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s]); rsd[s] = rs_of(deg_song_all[s]); rsdf[s] = rsf_of(deg_song_all[s]); }
+  // K2 work items: <= kSplitLen listeners each, longest first
+  struct Item { int song; long long begin; int len; uint8_t split; };
+  std::vector<Item> items;
+  for (int s = 0; s < S; ++s) {
+    const long long len = csc_ptr[s + 1] - csc_ptr[s];
+    for (long long o = 0; o < len; o += kSplitLen)
+      items.push_back({s, csc_ptr[s] + o, static_cast<int>(std::min<long long>(kSplitLen, len - o)), static_cast<uint8_t>(len > kSplitLen)});
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.len > b.len; });
+  h->n_items = static_cast<int>(items.size());
+  std::vector<int> it_song(items.size()), it_len(items.size());
+  std::vector<long long> it_begin(items.size());
+  std::vector<uint8_t> it_split(items.size());
+  for (size_t i = 0; i < items.size(); ++i) { it_song[i] = items[i].song; it_begin[i] = items[i].begin; it_len[i] = items[i].len; it_split[i] = items[i].split; }
+
+  std::vector<long long> trp(tr_rowptr, tr_rowptr + T + 1);
+  if ((rc = dev_upload(h, &h->d_tr_ptr, trp.data(), trp.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_tr_col, tr_col, static_cast<size_t>(nnz), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_csc_ptr, csc_ptr.data(), csc_ptr.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_csc_idx, csc_idx.data(), static_cast<size_t>(nnz), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_qv, qv.data(), qv.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_qd, qd.data(), qd.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rsd, rsd.data(), rsd.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rsv_f, rsvf.data(), rsvf.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rsd_f, rsdf.data(), rsdf.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_item_song, it_song.data(), it_song.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_item_begin, it_begin.data(), it_begin.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_item_len, it_len.data(), it_len.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_item_split, it_split.data(), it_split.size(), h->allocs))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));   // host staging vectors go out of scope below
+
+  // engine choice: dense operands A_tr (T x pitchS) and A_tr^T (S x pitchT) must fit comfortably
+  h->dense_bytes = static_cast<size_t>(T) * h->pitchS + static_cast<size_t>(S) * h->pitchT;
+  if (h->engine == MR_ENGINE_AUTO) {
+    size_t free_b = 0, total_b = 0;
+    MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    h->engine = (h->dense_bytes < free_b / 3) ? MR_ENGINE_TENSOR : MR_ENGINE_SPARSE;
+  }
+  if (h->engine == MR_ENGINE_TENSOR) {
+    if ((rc = dev_alloc(h, &h->d_Atr, static_cast<size_t>(T) * h->pitchS, h->allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_AtrT, static_cast<size_t>(S) * h->pitchT, h->allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_Ate, static_cast<size_t>(kUserBatch) * h->pitchS, h->allocs))) return rc;
+    PhaseTimer t(h, MR_T_EXPAND);
+    MR_LAUNCH(h, launch_expand_rows(h->d_tr_ptr, h->d_tr_col, nullptr, 0, T, T, h->pitchS, h->d_Atr, h->stream));
+    MR_LAUNCH(h, launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, nullptr, 0, S, S, h->pitchT, h->d_AtrT, h->stream));
+  } else {
+    h->dense_bytes = 0;
+  }
+  // per-batch workspaces
+  if ((rc = dev_alloc(h, &h->d_ct, static_cast<size_t>(T) * kUserBatch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
+  h->sel_pitch = (S + 63) / 64;
+  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kUserBatch) * h->sel_pitch, h->allocs))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->loaded = true;
+  if (n_test > 0) return mr_set_test_users(h, n_test, te_rowptr, te_col, deg_test, 0, 0);
+  return MR_OK;
+}
+
+int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const int32_t* te_col, const int32_t* deg_test,
+                      int64_t pair_index_base, int64_t n_pairs_total) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  if (n_test <= 0 || !deg_test) return fail(h, MR_ERR_BAD_ARG, "n_test must be > 0 and deg_test non-null");
+  int rc = check_csr(h, "test", n_test, h->S, te_rowptr, te_col);
+  if (rc) return rc;
+  for (int u = 0; u < n_test; ++u)
+    if (te_rowptr[u + 1] - te_rowptr[u] > 65535) return fail(h, MR_ERR_BAD_ARG, "test user %d has more than 65535 visible songs (u16 count panel)", u);
+  MR_CUDA(h, cudaSetDevice(h->device));
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (void* p : h->test_allocs) { cudaFree(p); }
+  h->test_allocs.clear();
+  h->have_test = false; h->have_topk = false; h->out_k = 0;
+  h->d_out_song = nullptr; h->d_out_score = nullptr; h->d_out_len = nullptr; h->d_dense = nullptr; h->d_cnt = nullptr; h->d_simf = nullptr;
+  const int U = n_test; const long long nnz = te_rowptr[U];
+  h->U = U; h->nnz_te = nnz;
+  h->h_te_ptr.assign(te_rowptr, te_rowptr + U + 1);
+  h->h_te_col.assign(te_col, te_col + nnz);
+  std::vector<double> rsa(U); std::vector<float> rsaf(U);
+  std::vector<long long> pair_base(static_cast<size_t>(U) + 1);
+  pair_base[0] = pair_index_base;
+  for (int u = 0; u < U; ++u) {
+    rsa[u] = rs_of(deg_test[u]); rsaf[u] = rsf_of(deg_test[u]);
+    pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
+  }
+  h->pair_index_base = pair_index_base;
+  h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
+  // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it
+  const int n_batches = (U + kUserBatch - 1) / kUserBatch;
+  std::vector<int> rows_all; std::vector<int> grow(static_cast<size_t>(std::max<long long>(nnz, 1)));
+  h->batch_row_off.assign(static_cast<size_t>(n_batches) + 1, 0);
+  h->max_batch_rows = 0;
+  for (int b = 0; b < n_batches; ++b) {
+    const long long e0 = te_rowptr[b * kUserBatch], e1 = te_rowptr[std::min(U, (b + 1) * kUserBatch)];
+    std::vector<int> uni(te_col + e0, te_col + e1);
+    std::sort(uni.begin(), uni.end());
+    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    for (long long e = e0; e < e1; ++e) grow[e] = static_cast<int>(std::lower_bound(uni.begin(), uni.end(), te_col[e]) - uni.begin());
+    rows_all.insert(rows_all.end(), uni.begin(), uni.end());
+    h->batch_row_off[b + 1] = static_cast<long long>(rows_all.size());
+    h->max_batch_rows = std::max<int>(h->max_batch_rows, static_cast<int>(uni.size()));
+  }
+  if ((rc = dev_upload(h, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size(), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rsa, rsa.data(), rsa.size(), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rsa_f, rsaf.data(), rsaf.size(), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_pair_base, pair_base.data(), pair_base.size(), h->test_allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_rows, rows_all.data(), rows_all.size(), h->test_allocs))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_test = true;
+  return MR_OK;
+}
+
+static int require_test(mr_handle* h) {
+  if (!h) return MR_ERR_STATE;
+  if (!h->loaded || !h->have_test) return fail(h, MR_ERR_STATE, "no data loaded (mr_load / mr_set_test_users)");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return MR_OK;
+}
+
+int mr_counts_ubm(mr_handle* h, int32_t* out_UxT) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (!out_UxT) return fail(h, MR_ERR_BAD_ARG, "null output");
+  if (!h->d_cnt && (rc = dev_alloc(h, &h->d_cnt, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+  BlendParams bp; memset(&bp, 0, sizeof bp);
+  return run_batches(h, MODEL_UBM, bp, 0, RUN_COUNTS_UBM, out_UxT);
+}
+
+int mr_similarity_ubm(mr_handle* h, float* out_UxT) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (!out_UxT) return fail(h, MR_ERR_BAD_ARG, "null output");
+  if (h->engine == MR_ENGINE_TENSOR) {
+    // cosine normalisation fused into the GEMM epilogue: out[b][v] = c / (sqrt|I_u| * sqrt|I_v|)   (MR:147-148)
+    if (!h->d_simf && (rc = dev_alloc(h, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+    for (int b0 = 0; b0 < h->U; b0 += kUserBatch) {
+      const int nb = std::min(kUserBatch, h->U - b0);
+      MR_LAUNCH(h, launch_expand_rows(h->d_te_ptr, h->d_te_col, nullptr, b0, nb, kUserBatch, h->pitchS, h->d_Ate, h->stream));
+      MR_LAUNCH(h, launch_count_gemm(h->d_Ate, kUserBatch, h->d_Atr, h->T, h->pitchS, nb, h->T, EPI_COS_F32, h->d_simf, h->T,
+                                     h->d_rsa_f + b0, h->d_rsv_f, h->num_sms, h->stream));
+      MR_CUDA(h, cudaMemcpyAsync(out_UxT + static_cast<long long>(b0) * h->T, h->d_simf, static_cast<size_t>(nb) * h->T * sizeof(float),
+                                 cudaMemcpyDeviceToHost, h->stream));
+      MR_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return MR_OK;
+  }
+  if (!h->d_simf && (rc = dev_alloc(h, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+  BlendParams bp; memset(&bp, 0, sizeof bp);
+  return run_batches(h, MODEL_UBM, bp, 0, RUN_SIM_UBM, out_UxT);
+}
+
+static int gram_range(mr_handle* h, int s0, int s1, int32_t* out_i32, float* out_f32) {
+  int rc = require_test(h);
+  if (rc == MR_ERR_STATE && h && h->loaded) rc = MR_OK;   // Gram rows need only the train replica
+  if (rc) return rc;
+  MR_CUDA(h, cudaSetDevice(h->device));
+  if (s0 < 0 || s1 > h->S || s0 > s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
+  const int chunk = 1024;
+  int* d_ids = nullptr; float* d_f = nullptr;
+  std::vector<void*> tmp;
+  if ((rc = dev_alloc(h, &d_ids, chunk, tmp))) return rc;
+  if (out_f32 && (rc = dev_alloc(h, &d_f, static_cast<size_t>(chunk) * h->S, tmp))) { free_list(tmp); return rc; }
+  if ((rc = ensure_gram_ws(h, chunk))) { free_list(tmp); return rc; }
+  for (int r0 = s0; r0 < s1; r0 += chunk) {
+    const int n = std::min(chunk, s1 - r0);
+    iota_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_ids, r0, n);
+    h->launches++;
+    if ((rc = gram_rows(h, d_ids, n))) { free_list(tmp); return rc; }
+    cudaError_t e;
+    if (out_i32) {
+      e = cudaMemcpy2DAsync(out_i32 + static_cast<long long>(r0 - s0) * h->S, static_cast<size_t>(h->S) * 4, h->d_g,
+                            static_cast<size_t>(h->ldg) * 4, static_cast<size_t>(h->S) * 4, n, cudaMemcpyDeviceToHost, h->stream);
+    } else {
+      gram_to_cos_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->d_g, h->ldg, d_ids, n, h->S, h->d_rsd_f, d_f);
+      h->launches++;
+      e = cudaMemcpyAsync(out_f32 + static_cast<long long>(r0 - s0) * h->S, d_f, static_cast<size_t>(n) * h->S * 4,
+                          cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { free_list(tmp); return fail(h, MR_ERR_CUDA, "gram rows copy-out: %s", cudaGetErrorString(e)); }
+  }
+  free_list(tmp);
+  return MR_OK;
+}
+
+int mr_counts_ibm(mr_handle* h, int s0, int s1, int32_t* out_rows) {
+  if (!out_rows) return fail(h, MR_ERR_BAD_ARG, "null output");
+  return gram_range(h, s0, s1, out_rows, nullptr);
+}
+int mr_similarity_ibm(mr_handle* h, int s0, int s1, float* out_rows) {
+  if (!out_rows) return fail(h, MR_ERR_BAD_ARG, "null output");
+  return gram_range(h, s0, s1, nullptr, out_rows);
+}
+
+int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
+  if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
+  if (!h->d_dense && (rc = dev_alloc(h, &h->d_dense, static_cast<size_t>(kUserBatch) * h->S, h->test_allocs))) return rc;
+  if (model == MR_IBM && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
+  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
+  return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
+}
+
+int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const double* ubm, const double* ibm, double* out,
+                   int64_t n_pairs, int64_t first_index, int64_t n_total) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (kind != MR_LC && kind != MR_AGG && kind != MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "mr_blend_dense: kind must be MR_LC, MR_AGG or MR_STOCH");
+  if (n_pairs < 0 || (n_pairs > 0 && (!ubm || !ibm || !out))) return fail(h, MR_ERR_BAD_ARG, "null arrays");
+  BlendParams bp;
+  int rc = make_blend_params(h, kind, param, seed, n_total > 0 ? n_total : n_pairs, &bp);
+  if (rc) return rc;
+  if (n_pairs == 0) return MR_OK;
+  MR_CUDA(h, cudaSetDevice(h->device));
+  std::vector<void*> tmp;
+  double *du = nullptr, *di = nullptr, *dout = nullptr;
+  if ((rc = dev_alloc(h, &du, n_pairs, tmp)) || (rc = dev_alloc(h, &di, n_pairs, tmp)) || (rc = dev_alloc(h, &dout, n_pairs, tmp))) { free_list(tmp); return rc; }
+  cudaError_t e = cudaMemcpyAsync(du, ubm, n_pairs * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(di, ibm, n_pairs * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    PhaseTimer t(h, MR_T_OTHER);
+    int lrc = launch_blend_arrays(bp, du, di, dout, n_pairs, first_index, h->stream);
+    h->launches++;
+    if (lrc) e = cudaErrorLaunchFailure;
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n_pairs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  free_list(tmp);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_blend_dense: %s", cudaGetErrorString(e));
+  return MR_OK;
+}
+
+int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (k < 1 || k > 1024) return fail(h, MR_ERR_BAD_ARG, "k must be in [1,1024], got %d", k);
+  BlendParams bp;
+  if ((rc = make_blend_params(h, model, param, seed, h->n_pairs_total, &bp))) return rc;
+  bp.pair_base = h->d_pair_base;
+  if (h->out_k != k) {
+    if ((rc = dev_alloc(h, &h->d_out_song, static_cast<size_t>(h->U) * k, h->test_allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_out_score, static_cast<size_t>(h->U) * k, h->test_allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_out_len, static_cast<size_t>(h->U), h->test_allocs))) return rc;
+    h->out_k = k;
+  }
+  if (model != MR_UBM && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
+  h->have_topk = false;
+  if ((rc = run_batches(h, model, bp, k, RUN_TOPK, nullptr))) return rc;
+  h->have_topk = true;
+  return MR_OK;
+}
+
+int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int32_t* out_len) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (!h->have_topk || h->out_k != k) return fail(h, MR_ERR_STATE, "no top-%d result on the device (call mr_topk_device first)", k);
+  if (!out_song || !out_score || !out_len) return fail(h, MR_ERR_BAD_ARG, "null output");
+  MR_CUDA(h, cudaMemcpyAsync(out_song, h->d_out_song, static_cast<size_t>(h->U) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  MR_CUDA(h, cudaMemcpyAsync(out_score, h->d_out_score, static_cast<size_t>(h->U) * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MR_CUDA(h, cudaMemcpyAsync(out_len, h->d_out_len, static_cast<size_t>(h->U) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MR_OK;
+}
+
+int mr_topk(mr_handle* h, int model, double param, uint64_t seed, int k, int32_t* out_song, double* out_score, int32_t* out_len) {
+  int rc = mr_topk_device(h, model, param, seed, k);
+  if (rc) return rc;
+  return mr_topk_fetch(h, k, out_song, out_score, out_len);
+}
+
+int mr_get_timing(mr_handle* h, double* ms_out, int n) {
+  if (!h || !ms_out) return MR_ERR_BAD_ARG;
+  for (int i = 0; i < n && i < MR_T_N; ++i) ms_out[i] = h->t_ms[i];
+  return MR_OK;
+}
+int mr_reset_timing(mr_handle* h) {
+  if (!h) return MR_ERR_BAD_ARG;
+  for (double& t : h->t_ms) t = 0;
+  return MR_OK;
+}
+int mr_get_info(mr_handle* h, int64_t* out, int n) {
+  if (!h || !out) return MR_ERR_BAD_ARG;
+  const int64_t v[6] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes)};
+  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  return MR_OK;
+}
+void* mr_stream(mr_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+}  // extern "C"
+#pragma GCC visibility pop

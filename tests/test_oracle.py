@@ -1,0 +1,171 @@
+"""CPU tests: the oracle against the golden vectors, the two restatements against each other, host-side logic."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from musicrecommendation_b200.dataset import fixture_4_3, synth, synth_config, CONFIGS
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def compact(a):
+    return a[~np.isnan(a)]
+
+
+def test_fixture_4_3_naive_is_exact(oracle_lib):
+    """the as-written restatement reproduces the hand-derived doubles bit for bit
+    (0.4999999999999999 pins sqrt(a)*sqrt(b) op order, 0.408... pins the train+test degree quirk)."""
+    fx = json.loads((GOLD / "fixture_4_3.json").read_text())
+    ds = fixture_4_3()
+    assert ds.n_pairs == 5 and ds.deg_song.tolist() == [2, 3, 2, 1]
+    u = oracle_lib.naive_scores(ds, oracle_lib.UBM)
+    i = oracle_lib.naive_scores(ds, oracle_lib.IBM)
+    assert compact(u).tolist() == fx["ubm"]
+    assert compact(i).tolist() == fx["ibm"]
+    assert compact(oracle_lib.blend_dense(oracle_lib.LC, 0.5, u, i)).tolist() == fx["lc_0.5"]
+    assert compact(oracle_lib.blend_dense(oracle_lib.AGG, 0.5, u, i)).tolist() == fx["agg_0.5"]
+    assert oracle_lib.counts_ubm(ds).tolist() == [fx["ubm_counts"]["X"], fx["ubm_counts"]["Y"]]
+    for m in (u, i):
+        assert oracle_lib.round_at(10, oracle_lib.evaluate(m, ds, 10)) == fx["map_rounded"]
+        assert oracle_lib.round_at(10, oracle_lib.evaluate(m, ds, 11)) == fx["map_rounded"]
+    names = ["s1", "s2", "s3", "s4"]
+    for key, m in (("ubm", u), ("ibm", i)):
+        song, _, ln = oracle_lib.topk(m, 2)
+        assert ln.tolist() == [2, 2]
+        assert [[names[s] for s in row] for row in song] == [fx["top2"][key]["X"], fx["top2"][key]["Y"]]
+
+
+def test_fixture_4_3_canonical_within_tolerance(oracle_lib):
+    fx = json.loads((GOLD / "fixture_4_3.json").read_text())
+    ds = fixture_4_3()
+    for key, m in (("ubm", oracle_lib.UBM), ("ibm", oracle_lib.IBM)):
+        c = compact(oracle_lib.canon_scores(ds, m))
+        np.testing.assert_allclose(c, fx[key], rtol=1e-5, atol=0)   # north_star tolerance: 1e-5 relative
+        assert np.max(np.abs(c - np.array(fx[key]))) < 1e-9
+
+
+def test_golden_small_seed11(oracle_lib):
+    g = np.load(GOLD / "small_seed11.npz")
+    ds = synth(T=40, U=6, S=500, seed=11)
+    for name, m in (("ubm", oracle_lib.UBM), ("ibm", oracle_lib.IBM)):
+        np.testing.assert_array_equal(oracle_lib.naive_scores(ds, m), g[f"naive_{name}"])
+        np.testing.assert_array_equal(oracle_lib.canon_scores(ds, m), g[f"canon_{name}"])
+        np.testing.assert_array_equal(oracle_lib.canon_sint(ds, m), g[f"sint_{name}"])
+    np.testing.assert_array_equal(oracle_lib.counts_ubm(ds), g["counts_ubm"])
+    np.testing.assert_array_equal(oracle_lib.gram_rows(ds, np.arange(64)), g["gram_0_64"])
+    s, v, l = oracle_lib.topk(g["canon_ubm"], 50)
+    np.testing.assert_array_equal(s, g["top50_ubm_song"])
+    np.testing.assert_array_equal(v, g["top50_ubm_score"])
+    np.testing.assert_array_equal(oracle_lib.blend_dense(oracle_lib.STOCH, 0.5, g["canon_ubm"], g["canon_ibm"], seed=42), g["stoch_seed42"])
+    assert oracle_lib.evaluate(g["canon_ubm"], ds) == float(g["map_ubm"])
+
+
+@pytest.mark.parametrize("seed,T,U,S", [(1, 30, 4, 300), (2, 80, 7, 1200), (3, 25, 3, 64)])
+def test_naive_vs_canonical_differential(oracle_lib, seed, T, U, S):
+    """The loop-for-loop transliteration and the CSR/integer restatement agree: same emitted pairs, scores within 1e-5
+    relative (measured ~1e-9), par == seq, and identical top-k away from near-ties."""
+    ds = synth(T=T, U=U, S=S, seed=seed)
+    for m in (oracle_lib.UBM, oracle_lib.IBM):
+        n = oracle_lib.naive_scores(ds, m)
+        npar = oracle_lib.naive_scores(ds, m, par=True)
+        c = oracle_lib.canon_scores(ds, m)
+        np.testing.assert_array_equal(n, npar)                       # "mAP should be the same between sequential and parallel"
+        np.testing.assert_array_equal(np.isnan(n), np.isnan(c))
+        np.testing.assert_array_equal(np.isnan(n), ds.listened_mask())
+        mask = ~np.isnan(n)
+        assert np.count_nonzero(mask) == ds.n_pairs
+        np.testing.assert_allclose(c[mask], n[mask], rtol=1e-5, atol=0)
+        np.testing.assert_array_equal(c[mask] == 0, n[mask] == 0)    # exact zeros stay exact zeros
+        assert oracle_lib.round_at(10, oracle_lib.evaluate(n, ds)) == oracle_lib.round_at(10, oracle_lib.evaluate(c, ds))
+
+
+def test_counts_match_dense_products(oracle_lib):
+    ds = synth(T=50, U=9, S=400, seed=5)
+    A_tr = np.zeros((ds.T, ds.S), np.int64)
+    A_tr[np.repeat(np.arange(ds.T), np.diff(ds.tr_ptr)), ds.tr_col] = 1
+    A_te = ds.listened_mask().astype(np.int64)
+    np.testing.assert_array_equal(oracle_lib.counts_ubm(ds), A_te @ A_tr.T)
+    rows = np.array([0, 5, 17, 399], np.int32)
+    np.testing.assert_array_equal(oracle_lib.gram_rows(ds, rows), (A_tr.T @ A_tr)[rows])
+    # canonical integers from the matrices
+    qv = np.array([oracle_lib.q(int(d)) for d in ds.deg_tr], np.int64)
+    qd = np.array([oracle_lib.q(int(d)) for d in ds.deg_song], np.int64)
+    np.testing.assert_array_equal(oracle_lib.canon_sint(ds, oracle_lib.UBM), ((A_te @ A_tr.T) * qv) @ A_tr)
+    G = A_tr.T @ A_tr
+    np.fill_diagonal(G, 0)
+    np.testing.assert_array_equal(oracle_lib.canon_sint(ds, oracle_lib.IBM), (A_te * qd) @ G)
+
+
+def test_java_random_stream(oracle_lib):
+    """java.util.Random known answers for seed 42 (widely published): nextInt() = -1170105035, nextDouble() =
+    0.7275636800328681 then 0.6832234717598454, nextFloat() = 0.7275637.  All are views of the same 48-bit LCG, so they
+    pin the multiplier / increment / seed scrambling of SURVEY A.4."""
+    mask = (1 << 48) - 1
+    st = (42 ^ 0x5DEECE66D) & mask
+    draws = []
+    for _ in range(4):
+        st = (st * 0x5DEECE66D + 0xB) & mask
+        draws.append(st)
+    as_int = draws[0] >> 16
+    assert (as_int - (1 << 32) if as_int >= (1 << 31) else as_int) == -1170105035
+    assert (((draws[0] >> 22) << 27) + (draws[1] >> 21)) * 2.0 ** -53 == 0.7275636800328681
+    assert (((draws[2] >> 22) << 27) + (draws[3] >> 21)) * 2.0 ** -53 == 0.6832234717598454
+    f = oracle_lib.java_random_floats(42, 3)
+    assert f[0] == np.float32(0.7275637) and f[2] == np.float32(0.6832234)
+    np.testing.assert_array_equal(f, [np.float32(d >> 24) / np.float32(1 << 24) for d in draws[:3]])
+    ubm = np.zeros(1000)
+    ibm = np.ones(1000)
+    out = oracle_lib.blend(oracle_lib.STOCH, 0.5, ubm, ibm, seed=42)
+    np.testing.assert_array_equal(out, (oracle_lib.java_random_floats(42, 1000).astype(np.float64) < 0.5).astype(np.float64))
+    # a shard starting at index 300 replays the same global stream
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.STOCH, 0.5, ubm[300:], ibm[300:], seed=42, first_index=300, n_total=1000), out[300:])
+
+
+def test_blend_semantics(oracle_lib):
+    ubm = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    ibm = np.array([10.0, 20.0, 30.0, 40.0, 50.0])
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.LC, 0.25, ubm, ibm), ubm * 0.25 + ibm * (1 - 0.25))
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.AGG, 0.5, ubm, ibm), [10, 20, 3, 4, 5])     # (0.5*5).toInt = 2
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.AGG, 1.0, ubm, ibm), ibm)
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.AGG, 0.0, ubm, ibm), ubm)
+    np.testing.assert_array_equal(oracle_lib.blend(oracle_lib.LC, 7.0, ubm, ibm), ubm * 7.0 + ibm * (1 - 7.0))   # LC has no range check (MR:317-330)
+    for kind in (oracle_lib.AGG, oracle_lib.STOCH):
+        for bad in (-0.01, 1.01):
+            with pytest.raises(ValueError, match="between 0 and 1"):
+                oracle_lib.blend(kind, bad, ubm, ibm)
+    assert len(oracle_lib.blend(oracle_lib.LC, 0.5, ubm, ibm[:3])) == 3       # zip truncates (MR:322)
+
+
+def test_evaluate_degenerate(oracle_lib):
+    ds = fixture_4_3()
+    flat = np.where(ds.listened_mask(), np.nan, 0.25)       # max == min -> NaN comparisons -> no predictions -> mAP 0
+    assert oracle_lib.evaluate(flat, ds) == 0.0
+
+
+def test_topk_ties_and_short_rows(oracle_lib):
+    s = np.array([[0.5, np.nan, 0.5, 0.0, 0.5], [np.nan, np.nan, np.nan, 1.0, np.nan]])
+    song, val, ln = oracle_lib.topk(s, 4)
+    assert song[0].tolist() == [0, 2, 4, 3] and ln.tolist() == [4, 1]
+    assert song[1].tolist() == [3, -1, -1, -1] and val[1].tolist() == [1.0, 0, 0, 0]
+
+
+def test_synth_shapes():
+    for name in ("c1", "c2"):
+        ds = synth_config(name)
+        cfg = CONFIGS[name]
+        assert (ds.T, ds.U, ds.S) == (cfg["T"], cfg["U"], cfg["S"])
+        assert ds.deg_song.min() >= 1                               # every song is heard in train ∪ test-visible
+        for ptr, col in ((ds.tr_ptr, ds.tr_col), (ds.te_ptr, ds.te_col)):
+            d = np.diff(col)
+            starts = ptr[1:-1]
+            inner = np.ones(len(col) - 1, bool)
+            inner[starts[starts < len(col)] - 1] = False
+            assert np.all(d[inner] > 0)                             # rows ascending, no duplicate (user, song)
+        assert np.all(np.diff(ds.lab_ptr) >= 1)
+        vis = set(zip(np.repeat(np.arange(ds.U), np.diff(ds.te_ptr)).tolist(), ds.te_col.tolist()))
+        lab = set(zip(np.repeat(np.arange(ds.U), np.diff(ds.lab_ptr)).tolist(), ds.lab_col.tolist()))
+        assert not (vis & lab)
+    again = synth_config("c1")
+    np.testing.assert_array_equal(again.tr_col, synth_config("c1").tr_col)
