@@ -112,6 +112,7 @@ int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int
 enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5, MR_T_N = 6 };
 int mr_get_timing(mr_handle* h, double* ms_out, int n);      /* accumulated CUDA-event ms per phase since the last reset */
 int mr_reset_timing(mr_handle* h);
+int mr_set_profile(mr_handle* h, int on);                   /* toggle MR_PROFILE at run time (it synchronises after every phase) */
 int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated] */
 void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
 

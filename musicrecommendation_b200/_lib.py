@@ -16,7 +16,7 @@ TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other"]
 # every symbol include/mrscore.h declares
 SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_counts_ubm", "mr_counts_ibm",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_topk", "mr_topk_device",
-           "mr_topk_fetch", "mr_get_timing", "mr_reset_timing", "mr_get_info", "mr_stream"]
+           "mr_topk_fetch", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
 
 _lib = None
 
@@ -56,6 +56,7 @@ def load():
     lib.mr_topk_fetch.argtypes = [vp, i32, vp, vp, vp]
     lib.mr_get_timing.argtypes = [vp, vp, i32]
     lib.mr_reset_timing.argtypes = [vp]
+    lib.mr_set_profile.argtypes = [vp, i32]
     lib.mr_get_info.argtypes = [vp, vp, i32]
     lib.mr_stream.argtypes = [vp]
     lib.mr_stream.restype = vp

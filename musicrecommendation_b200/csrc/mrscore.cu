@@ -676,6 +676,11 @@ int mr_get_info(mr_handle* h, int64_t* out, int n) {
   for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
   return MR_OK;
 }
+int mr_set_profile(mr_handle* h, int on) {
+  if (!h) return MR_ERR_BAD_ARG;
+  if (on) h->flags |= MR_PROFILE; else h->flags &= ~static_cast<unsigned>(MR_PROFILE);
+  return MR_OK;
+}
 void* mr_stream(mr_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 
 }  // extern "C"
