@@ -158,12 +158,12 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         } else if constexpr (EPI == EPI_U16_T) {
-          // Ct[n][m]: the 32 lanes of a warp hold 32 consecutive m -> 64 B coalesced stores per column
-          if (m < p.ld) {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(n0) * p.ld + m;
+          // Ct[n][m] (p.ld = 128): the 32 lanes of a warp hold 32 consecutive m -> one 64-byte store per column n
+          if (m < kUserBatch) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(n0) * kUserBatch + m;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) dst[static_cast<long long>(j) * p.ld] = static_cast<uint16_t>(r[j] > 65535u ? 65535u : r[j]);
+              if (n0 + j < p.N) dst[j * kUserBatch] = static_cast<uint16_t>(r[j] > 65535u ? 65535u : r[j]);
           }
         } else {  // EPI_COS_F32
           if (m < p.M) {

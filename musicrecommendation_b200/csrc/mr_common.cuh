@@ -6,9 +6,14 @@
 
 namespace mr {
 
-// Fixed-point scale of the canonical arithmetic: q(deg) = rint(2^31 / sqrt(deg)).
-constexpr double kQScale = 2147483648.0;          // 2^31
-constexpr double kQInv = 1.0 / 2147483648.0;      // 2^-31
+// Fixed-point scales of the canonical arithmetic: q(deg) = rint(scale / sqrt(deg)).
+//   UBM: 2^31 — q(1) = 2^31 fits a u32; a term count * q <= sqrt(deg) * 2^31 fits u64 with 2^22 train users to spare.
+//   IBM: 2^26 — the user-space weighted count sum_{j in I_u ∩ I_v} q(d_j) stays below 2^32 for up to 90 shared songs, so the
+//               gathered panel holds u32 entries (wrap-arounds are recorded as carry events and repaired exactly).
+constexpr double kQScaleUbm = 2147483648.0;       // 2^31
+constexpr double kQInvUbm = 1.0 / 2147483648.0;
+constexpr double kQScaleIbm = 67108864.0;         // 2^26
+constexpr double kQInvIbm = 1.0 / 67108864.0;
 constexpr long long kListened = -1;               // sentinel written into Sint at listened (u, s) pairs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

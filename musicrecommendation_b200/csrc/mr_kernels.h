@@ -5,7 +5,13 @@
 
 namespace mr {
 
-constexpr int kUserBatch = 128;   // test users per batch = UMMA M = 4 users per lane in the K2 gather
+constexpr int kUserBatch = 128;   // test users per batch = UMMA M
+// Count panels K1 hands to K2, train-user-major so that one gathered row serves the whole 128-user batch in one coalesced read:
+//   UBM  u16 Ct[T][128]   256-byte rows     IBM (user space)  u32 Wi[T][128]   512-byte rows
+// (A sub-panel-major variant with 32-byte, L2-resident rows was measured 1.7-1.9x slower on B200: random 32-byte sector
+//  gathers out of L2 lose more than the saved HBM traffic gains — profiles/r01_notes.md.)
+__host__ __device__ inline long long ct_index(long long T, int v, int b) { (void)T; return static_cast<long long>(v) * kUserBatch + b; }
+__host__ __device__ inline long long wi_index(long long T, int v, int b) { (void)T; return static_cast<long long>(v) * kUserBatch + b; }
 
 enum { EPI_I32 = 0, EPI_U16_T = 1, EPI_COS_F32 = 2 };
 enum { MODEL_UBM = 0, MODEL_IBM = 1, MODEL_LC = 2, MODEL_AGG = 3, MODEL_STOCH = 4 };
@@ -19,6 +25,14 @@ int launch_expand_rows(const long long* ptr, const int* idx, const int* rows, in
 // ---- K1s (k1_sparse_count.cu): the same counts from the inverted index, for shapes whose dense operands do not fit
 int launch_sparse_count_u16t(const long long* te_ptr, const int* te_col, int u0, int n_users, const long long* csc_ptr,
                              const int* csc_idx, uint16_t* ct, long long n_train, cudaStream_t st);
+struct CarryList {            // wrap-arounds of the u32 weighted-count panel: (v, b) pairs, repaired by launch_carry_fixup
+  unsigned int* count;        // [1]
+  uint2* events;              // [capacity]
+  unsigned int capacity;
+};
+int launch_sparse_wcount_u32(const long long* te_ptr, const int* te_col, int u0, int n_users, const long long* csc_ptr,
+                             const int* csc_idx, const uint32_t* qd, uint32_t* wi, long long n_train, CarryList carry, cudaStream_t st);
+int launch_carry_fixup(CarryList carry, const long long* tr_ptr, const int* tr_col, long long* sint, long long spitch, cudaStream_t st);
 int launch_sparse_gram_rows(const int* rows, int n_rows, const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr,
                             const int* tr_col, int32_t* g, long long ldg, cudaStream_t st);
 
@@ -30,7 +44,9 @@ struct AggItems {            // work list over the train inverted index: one war
   const uint8_t* split;      // [n_items] 1 -> the song is covered by several items (accumulate atomically)
   int n_items;
 };
-int launch_aggregate_ubm(const AggItems& items, const int* csc_idx, const uint32_t* qv, const uint16_t* ct, long long* sint,
+int launch_aggregate_ubm(const AggItems& items, const int* csc_idx, const uint32_t* qv, const uint16_t* ct, long long n_train,
+                         long long* sint, long long spitch, int num_sms, cudaStream_t st);
+int launch_aggregate_w32(const AggItems& items, const int* csc_idx, const uint32_t* wi, long long n_train, long long* sint,
                          long long spitch, int num_sms, cudaStream_t st);
 int launch_aggregate_ibm(const long long* te_ptr, const int* te_col, const int* te_grow, const uint32_t* qd, int u0, int n_users,
                          const int32_t* g, long long ldg, int n_songs, long long* sint, long long spitch, cudaStream_t st);

@@ -54,6 +54,8 @@ struct mr_handle {
   long long pair_index_base = 0, n_pairs_total = 0;
   // workspaces
   uint8_t *d_Ate = nullptr, *d_Aj = nullptr; uint16_t* d_ct = nullptr; long long *d_sint_u = nullptr, *d_sint_i = nullptr;
+  uint32_t* d_wi = nullptr;             // IBM user-space weighted counts u32[T][128] (sparse engine)
+  unsigned int* d_carry_count = nullptr; uint2* d_carry_events = nullptr; unsigned int carry_cap = 1u << 20; unsigned int* h_carry_seen = nullptr;
   uint64_t* d_sel = nullptr; long long sel_pitch = 0; int32_t* d_g = nullptr; size_t g_bytes = 0; size_t aj_bytes = 0;
   double* d_dense = nullptr; int32_t* d_cnt = nullptr; float* d_simf = nullptr;
   // results
@@ -108,8 +110,8 @@ int dev_upload(mr_handle* h, Tp** out, const Tp* src, size_t count, std::vector<
   return MR_OK;
 }
 
-inline uint32_t q_of(int32_t deg) { return deg <= 0 ? 0u : static_cast<uint32_t>(llrint(kQScale / std::sqrt(static_cast<double>(deg)))); }
-inline double rs_of(int32_t deg) { return deg <= 0 ? 0.0 : kQInv / std::sqrt(static_cast<double>(deg)); }
+inline uint32_t q_of(int32_t deg, double scale) { return deg <= 0 ? 0u : static_cast<uint32_t>(llrint(scale / std::sqrt(static_cast<double>(deg)))); }
+inline double rs_of(int32_t deg, double inv) { return deg <= 0 ? 0.0 : inv / std::sqrt(static_cast<double>(deg)); }
 inline float rsf_of(int32_t deg) { return deg <= 0 ? 0.0f : static_cast<float>(1.0 / std::sqrt(static_cast<double>(deg))); }
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
@@ -145,7 +147,7 @@ __global__ void ct_to_i32_kernel(const uint16_t* __restrict__ ct, int n_train, i
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(nb) * n_train;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / n_train), v = static_cast<int>(i % n_train);
-    out[i] = ct[static_cast<long long>(v) * kUserBatch + b];
+    out[i] = ct[ct_index(n_train, v, b)];
   }
 }
 __global__ void ct_to_cos_kernel(const uint16_t* __restrict__ ct, int n_train, int nb, const float* __restrict__ rsa,
@@ -153,7 +155,7 @@ __global__ void ct_to_cos_kernel(const uint16_t* __restrict__ ct, int n_train, i
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(nb) * n_train;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / n_train), v = static_cast<int>(i % n_train);
-    out[i] = static_cast<float>(ct[static_cast<long long>(v) * kUserBatch + b]) * (rsa[b] * rsv[v]);
+    out[i] = static_cast<float>(ct[ct_index(n_train, v, b)]) * (rsa[b] * rsv[v]);
   }
 }
 __global__ void gram_to_cos_kernel(const int32_t* __restrict__ g, long long ldg, const int* __restrict__ rows, int n_rows, int n_songs,
@@ -260,9 +262,22 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       PhaseTimer t(h, MR_T_AGG_UBM);
       MR_CUDA(h, cudaMemsetAsync(h->d_sint_u, 0, static_cast<size_t>(kUserBatch) * h->spitch * sizeof(long long), h->stream));
       AggItems items{h->d_item_song, h->d_item_begin, h->d_item_len, h->d_item_split, h->n_items};
-      MR_LAUNCH(h, launch_aggregate_ubm(items, h->d_csc_idx, h->d_qv, h->d_ct, h->d_sint_u, h->spitch, h->num_sms, h->stream));
+      MR_LAUNCH(h, launch_aggregate_ubm(items, h->d_csc_idx, h->d_qv, h->d_ct, h->T, h->d_sint_u, h->spitch, h->num_sms, h->stream));
     }
-    if (need_ibm) {
+    if (need_ibm && h->engine == MR_ENGINE_SPARSE) {
+      // user-space formulation: weighted intersection counts, then the same inverted-index gather as UBM
+      CarryList carry{h->d_carry_count, h->d_carry_events, h->carry_cap};
+      {
+        PhaseTimer t(h, MR_T_COUNT);
+        MR_LAUNCH(h, launch_sparse_wcount_u32(h->d_te_ptr, h->d_te_col, b0, nb, h->d_csc_ptr, h->d_csc_idx, h->d_qd, h->d_wi, h->T, carry, h->stream));
+      }
+      PhaseTimer t(h, MR_T_AGG_IBM);
+      MR_CUDA(h, cudaMemsetAsync(h->d_sint_i, 0, static_cast<size_t>(kUserBatch) * h->spitch * sizeof(long long), h->stream));
+      AggItems items{h->d_item_song, h->d_item_begin, h->d_item_len, h->d_item_split, h->n_items};
+      MR_LAUNCH(h, launch_aggregate_w32(items, h->d_csc_idx, h->d_wi, h->T, h->d_sint_i, h->spitch, h->num_sms, h->stream));
+      MR_LAUNCH(h, launch_carry_fixup(carry, h->d_tr_ptr, h->d_tr_col, h->d_sint_i, h->spitch, h->stream));
+      MR_CUDA(h, cudaMemcpyAsync(h->h_carry_seen + (b0 / kUserBatch) % 4096, h->d_carry_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    } else if (need_ibm) {
       const int batch = b0 / kUserBatch;
       const long long r_off = h->batch_row_off[batch];
       const int n_rows = static_cast<int>(h->batch_row_off[batch + 1] - r_off);
@@ -290,6 +305,14 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
                                (model == MODEL_AGG || model == MODEL_STOCH) ? h->d_sel : nullptr, h->sel_pitch, b0, nb, h->S, h->d_rsa,
                                h->d_rsd, k, h->d_out_song, h->d_out_score, h->d_out_len, h->stream));
     }
+  }
+  if (need_ibm && h->engine == MR_ENGINE_SPARSE) {
+    // the carry list of the u32 weighted-count panel must not have overflowed (it never does on real data: an event needs
+    // more than ~64 songs shared between one test user and one train user)
+    MR_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4096; ++i)
+      if (h->h_carry_seen[i] > h->carry_cap)
+        return fail(h, MR_ERR_OOM, "IBM weighted-count carry list overflowed (%u events > capacity %u)", h->h_carry_seen[i], h->carry_cap);
   }
   return MR_OK;
 }
@@ -346,6 +369,7 @@ void mr_destroy(mr_handle* h) {
   if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
   free_list(h->test_allocs);
   free_list(h->allocs);
+  if (h->h_carry_seen) cudaFreeHost(h->h_carry_seen);
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
   if (h->ev[1]) cudaEventDestroy(h->ev[1]);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -384,8 +408,8 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<uint32_t> qv(T), qd(S);
   std::vector<double> rsd(S);
   std::vector<float> rsvf(T), rsdf(S);
-  for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v]); rsvf[v] = rsf_of(deg_train[v]); }
-  for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s]); rsd[s] = rs_of(deg_song_all[s]); rsdf[s] = rsf_of(deg_song_all[s]); }
+  for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); }
+  for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s], kQScaleIbm); rsd[s] = rs_of(deg_song_all[s], kQInvIbm); rsdf[s] = rsf_of(deg_song_all[s]); }
   // K2 work items: <= kSplitLen listeners each, longest first
   struct Item { int song; long long begin; int len; uint8_t split; };
   std::vector<Item> items;
@@ -436,6 +460,13 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   }
   // per-batch workspaces
   if ((rc = dev_alloc(h, &h->d_ct, static_cast<size_t>(T) * kUserBatch, h->allocs))) return rc;
+  if (h->engine == MR_ENGINE_SPARSE) {
+    if ((rc = dev_alloc(h, &h->d_wi, static_cast<size_t>(T) * kUserBatch, h->allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_carry_count, 1, h->allocs))) return rc;
+    if ((rc = dev_alloc(h, &h->d_carry_events, h->carry_cap, h->allocs))) return rc;
+    MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_carry_seen), 4096 * sizeof(unsigned int)));
+    memset(h->h_carry_seen, 0, 4096 * sizeof(unsigned int));
+  }
   if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
   if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
   h->sel_pitch = (S + 63) / 64;
@@ -468,7 +499,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   std::vector<long long> pair_base(static_cast<size_t>(U) + 1);
   pair_base[0] = pair_index_base;
   for (int u = 0; u < U; ++u) {
-    rsa[u] = rs_of(deg_test[u]); rsaf[u] = rsf_of(deg_test[u]);
+    rsa[u] = rs_of(deg_test[u], kQInvUbm); rsaf[u] = rsf_of(deg_test[u]);
     pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
   }
   h->pair_index_base = pair_index_base;
@@ -589,7 +620,7 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
   if (!h->d_dense && (rc = dev_alloc(h, &h->d_dense, static_cast<size_t>(kUserBatch) * h->S, h->test_allocs))) return rc;
-  if (model == MR_IBM && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
+  if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
   return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
 }
@@ -635,7 +666,7 @@ int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) 
     if ((rc = dev_alloc(h, &h->d_out_len, static_cast<size_t>(h->U), h->test_allocs))) return rc;
     h->out_k = k;
   }
-  if (model != MR_UBM && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
+  if (model != MR_UBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   h->have_topk = false;
   if ((rc = run_batches(h, model, bp, k, RUN_TOPK, nullptr))) return rc;
   h->have_topk = true;

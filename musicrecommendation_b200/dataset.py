@@ -74,10 +74,21 @@ class Dataset:
                        dict(self.meta, shard=(u0, u1)))
 
 
+def _sorted_unique(key: np.ndarray) -> np.ndarray:
+    """np.unique for int64 keys via sort + adjacent compare (numpy 2.3's hash-based unique is ~6x slower at 5e7 keys)."""
+    key = np.sort(key)
+    if len(key) == 0:
+        return key
+    keep = np.empty(len(key), bool)
+    keep[0] = True
+    np.not_equal(key[1:], key[:-1], out=keep[1:])
+    return key[keep]
+
+
 def _csr_from_pairs(rows: np.ndarray, cols: np.ndarray, n_rows: int):
     """Sort (row, col) pairs, drop duplicates, return (ptr int64, col int32)."""
     key = rows.astype(np.int64) * (1 << 32) | cols.astype(np.int64)
-    key = np.unique(key)
+    key = _sorted_unique(key)
     r = (key >> 32).astype(np.int64)
     c = (key & 0xFFFFFFFF).astype(np.int32)
     ptr = np.zeros(n_rows + 1, np.int64)
@@ -136,7 +147,7 @@ def synth(T: int, U: int, S: int, seed: int, mean_deg: float = 47.5, with_string
 
     # de-duplicate (user, song) rows
     def dedupe(rows, ranks):
-        key = np.unique(rows * (1 << 32) | ranks)
+        key = _sorted_unique(rows * (1 << 32) | ranks)
         return key >> 32, key & 0xFFFFFFFF
     tr_rows, tr_rank = dedupe(tr_rows, tr_rank)
     te_rows, te_rank = dedupe(te_rows, te_rank)
@@ -159,7 +170,7 @@ def synth(T: int, U: int, S: int, seed: int, mean_deg: float = 47.5, with_string
             tr_rows = np.concatenate([tr_rows, rng.integers(0, T, size=len(rest))])
             tr_rank = np.concatenate([tr_rank, rest])
     # labels: drop the ones the user already has in the visible half; keep at least one per user
-    lab_key = np.unique(lab_rows * (1 << 32) | lab_rank)
+    lab_key = _sorted_unique(lab_rows * (1 << 32) | lab_rank)
     vis_key = te_rows * (1 << 32) | te_rank
     lab_key = lab_key[~np.isin(lab_key, vis_key)]
     lab_rows, lab_rank = lab_key >> 32, lab_key & 0xFFFFFFFF

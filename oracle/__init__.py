@@ -55,9 +55,9 @@ def lib():
             build()
         _lib = C.CDLL(str(_SO))
         _lib.mro_q.restype = C.c_int64
-        _lib.mro_q.argtypes = [C.c_int32]
+        _lib.mro_q.argtypes = [C.c_int32, C.c_int]
         _lib.mro_rs.restype = C.c_double
-        _lib.mro_rs.argtypes = [C.c_int32]
+        _lib.mro_rs.argtypes = [C.c_int32, C.c_int]
         _lib.mro_num_threads.restype = C.c_int
         _lib.mro_naive_sample.restype = C.c_int64
         _lib.mro_evaluate.restype = C.c_double
@@ -88,8 +88,8 @@ def set_threads(n: int) -> None:
     os.environ["OMP_NUM_THREADS"] = str(n)
 
 
-def q(deg: int) -> int:
-    return int(lib().mro_q(int(deg)))
+def q(deg: int, model: int = UBM) -> int:
+    return int(lib().mro_q(int(deg), int(model)))
 
 
 def naive_scores(ds, model: int, par: bool = False) -> np.ndarray:

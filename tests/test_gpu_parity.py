@@ -122,6 +122,13 @@ def test_synthetic_parity(engine, oracle_lib, T, U, S, seed):
     check_dataset(synth(T=T, U=U, S=S, seed=seed), oracle_lib, engine, k=min(500, S))
 
 
+def test_popular_songs_split_across_warps(engine, oracle_lib):
+    """Songs with more than 4096 train listeners are aggregated by several warps with 64-bit integer atomics: still exact."""
+    ds = synth(T=12000, U=200, S=30000, seed=6)
+    assert np.bincount(ds.tr_col).max() > 4096
+    check_dataset(ds, oracle_lib, engine, blends=False)
+
+
 def test_config_c1(engine, oracle_lib):
     ds = synth_config("c1")
     info = check_dataset(ds, oracle_lib, engine)

@@ -43,7 +43,7 @@ def test_fixture_4_3_canonical_within_tolerance(oracle_lib):
     for key, m in (("ubm", oracle_lib.UBM), ("ibm", oracle_lib.IBM)):
         c = compact(oracle_lib.canon_scores(ds, m))
         np.testing.assert_allclose(c, fx[key], rtol=1e-5, atol=0)   # north_star tolerance: 1e-5 relative
-        assert np.max(np.abs(c - np.array(fx[key]))) < 1e-9
+        assert np.max(np.abs(c - np.array(fx[key]))) < 1e-7   # measured: ~4e-12 (UBM, 2^31 scale), ~5e-9 (IBM, 2^26 scale)
 
 
 def test_golden_small_seed11(oracle_lib):
@@ -91,7 +91,7 @@ def test_counts_match_dense_products(oracle_lib):
     np.testing.assert_array_equal(oracle_lib.gram_rows(ds, rows), (A_tr.T @ A_tr)[rows])
     # canonical integers from the matrices
     qv = np.array([oracle_lib.q(int(d)) for d in ds.deg_tr], np.int64)
-    qd = np.array([oracle_lib.q(int(d)) for d in ds.deg_song], np.int64)
+    qd = np.array([oracle_lib.q(int(d), oracle_lib.IBM) for d in ds.deg_song], np.int64)
     np.testing.assert_array_equal(oracle_lib.canon_sint(ds, oracle_lib.UBM), ((A_te @ A_tr.T) * qv) @ A_tr)
     G = A_tr.T @ A_tr
     np.fill_diagonal(G, 0)
