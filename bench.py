@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="msd", choices=["msd", "c1", "c2", "c3"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "sparse"])
+    ap.add_argument("--space", default="auto", choices=["auto", "user", "item"])
     ap.add_argument("--ref-users", type=int, default=96, help="test users per step of the CPU port sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--users", type=int, default=0, help="profiling aid: score only the first N test users of the shard (not a bench line)")
@@ -179,6 +180,7 @@ def main():
 
     from musicrecommendation_b200 import _lib
     from musicrecommendation_b200.recommender import MusicRecommender
+    from musicrecommendation_b200.distributed import gather_topk
 
     ds, desc = make_workload(args.workload, rank, world)
     if args.users:
@@ -186,7 +188,8 @@ def main():
         desc += f" [PROFILING SUBSET: first {ds.U} test users]"
     engine = {"auto": _lib.MR_ENGINE_AUTO, "tensor": _lib.MR_ENGINE_TENSOR, "sparse": _lib.MR_ENGINE_SPARSE}[args.engine]
     t0 = time.time()
-    mr = MusicRecommender(ds, device=local_rank, engine=engine)
+    space = {"auto": _lib.MR_SPACE_AUTO, "user": _lib.MR_SPACE_USER, "item": _lib.MR_SPACE_ITEM}[args.space]
+    mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space)
     lib, h = mr._lib, mr._h
     log(f"[rank {rank}] mr_load done in {time.time() - t0:.1f}s, info={mr.info()}")
     stream = torch.cuda.ExternalStream(int(lib.mr_stream(h)), device=local_rank)
@@ -233,12 +236,19 @@ def main():
     def p(a):
         return C.c_void_p(a.ctypes.data)
 
-    def step_e2e():
+    def step_e2e(verbose=False):
+        t_a = time.perf_counter()
         check(lib.mr_set_test_users(h, U, p(keep[0][1]), p(keep[1][1]), p(keep[2][1]), base, 0))
+        t_b = time.perf_counter()
         for model in (_lib.MR_UBM, _lib.MR_IBM):
             check(lib.mr_topk(h, model, 0.0, 0, k, p(out[0][1]), p(out[1][1]), p(out[2][1])))
+            if world > 1:   # the reference's `.collect` (DIST:451-478): all-gather the fixed-size top-k blocks over NCCL
+                torch.cuda.current_stream().wait_stream(stream)
+                gather_topk(*mr.topk_device_tensors(k), U * world, world, rank)
+        if verbose:
+            log(f"[rank {rank}] e2e step: mr_set_test_users {1e3 * (t_b - t_a):.1f} ms, 2 x mr_topk {1e3 * (time.perf_counter() - t_b):.1f} ms")
 
-    step_e2e()
+    step_e2e(verbose=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -278,31 +288,44 @@ def main():
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        # dominant phase and its algorithmic bytes per launch: every operand crosses HBM once
+        # dominant phase and its algorithmic bytes per launch: every operand crosses HBM once per launch
         T, nnz = ds.T, ds.nnz_tr
         sparse = info["engine"] == _lib.MR_ENGINE_SPARSE
+        item = info["space"] == _lib.MR_SPACE_ITEM
+        Sp = (S + 31) // 32 * 32
+        n_launch = {"agg_ubm": n_batches, "agg_ibm": n_batches, "topk": 2 * n_batches, "count": 2 * n_batches, "expand": n_batches,
+                    "head_rowsum": 2 * n_batches, "tail_scatter": 2 * n_batches}
         alg = {
+            # user space: count panel + inverted index + q table + Sint panel written
             "agg_ubm": 2 * 128 * T + 4 * nnz + 8 * (S + 1) + 4 * T + 8 * 128 * S,
             "agg_ibm": (4 * 128 * T + 4 * nnz + 8 * (S + 1) + 8 * 128 * S) if sparse else None,
-            "topk": 2 * 8 * 128 * S / 2 + 12 * 128 * k,      # one Sint panel read per model pass + top-k written
+            # item space: per step every (test user, head song) entry reads one Gq row (8 B/song) in the UBM pass and one G row
+            # (4 B/song) in the IBM pass, and each pass writes its Sint rows; averaged over the 2 * n_batches launches
+            "head_rowsum": (info["head_entries"] * Sp * 12 + 2 * U * Sp * 8) / (2 * n_batches),
+            # top-k: three streaming passes over the user's Sint row(s) + rsd for IBM, k results written
+            "topk": (3 * U * S * 8 * 2 + 3 * U * S * 8 + 2 * 12 * U * k) / (2 * n_batches),
         }
-        dom = max(("agg_ubm", "agg_ibm", "topk", "count", "expand"), key=lambda n: phases.get(n, 0.0))
-        launches_of = {"agg_ubm": n_batches, "agg_ibm": n_batches, "topk": 2 * n_batches, "count": 2 * n_batches, "expand": n_batches}
-        dom_ms = phases[dom] / launches_of[dom]
-        roof = {"bound": "hbm", "kernel": {"agg_ubm": "aggregate_panel_kernel<true>", "agg_ibm": "aggregate_panel_kernel<false>" if sparse else "aggregate_ibm_kernel",
-                                           "topk": "topk_kernel", "count": "sparse_count / count_gemm", "expand": "expand_rows_kernel"}[dom],
-                "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                "ms_per_launch": dom_ms, "phase_ms_per_step": phases}
+        names = {"agg_ubm": "aggregate_panel_kernel<true>", "agg_ibm": "aggregate_panel_kernel<false>" if sparse else "aggregate_ibm_kernel",
+                 "topk": "topk_kernel", "count": "sparse_count / count_gemm", "expand": "expand_rows_kernel",
+                 "head_rowsum": "head_rowsum_kernel", "tail_scatter": "tail_scatter_kernel"}
+        dom = max(n_launch, key=lambda n: phases.get(n, 0.0))
+        dom_ms = phases[dom] / n_launch[dom]
+        roof = {"bound": "hbm", "kernel": names[dom], "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": dom_ms, "launches_per_step": n_launch[dom], "phase_ms_per_step": phases}
         if alg.get(dom):
             roof["achieved"] = alg[dom] / (dom_ms * 1e-3) / 1e9
             roof["frac"] = roof["achieved"] / hbm_peak
             roof["algorithmic_bytes_per_launch"] = alg[dom]
+        traffic_file = ROOT / "profiles" / "traffic.json"      # dram bytes per launch from the committed ncu --set full capture
+        if traffic_file.exists():
+            roof["traffic"] = json.loads(traffic_file.read_text()).get(names[dom])
         line = {
             "metric": "scored (test-user, song) pairs/sec, UBM+IBM with top-500", "value": pairs_all * args.steps / (dev_ms_max * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
             "config": {"workload": desc, "k": K_TOP, "engine": ["auto", "tensor", "sparse"][info["engine"]],
-                       "l2": "inputs (train CSC + count panels, >1 GB per batch) exceed the 126 MB L2; no explicit flush",
+                       "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"],
+                       "l2": "inputs (precomputed head rows >= 10 GB, train CSR/CSC 0.7 GB, 0.8 GB of Sint panels per batch) exceed the 126 MB L2; no explicit flush",
                        "pairs_per_step": pairs_all},
             "e2e": {"value": pairs_all * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps},

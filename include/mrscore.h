@@ -55,7 +55,12 @@ enum {
   MR_ENGINE_TENSOR = 1,   /* force K1 = tcgen05 int8 GEMM */
   MR_ENGINE_SPARSE = 2,   /* force K1s = inverted-index counts */
   MR_ENGINE_MASK = 3,
-  MR_PROFILE = 4          /* record CUDA events around every kernel phase (mr_get_timing) */
+  MR_PROFILE = 4,         /* record CUDA events around every kernel phase (mr_get_timing) */
+  /* scoring formulation (bit-identical results) */
+  MR_SPACE_AUTO = 0,      /* item space when the test shard has >= 1024 users, else user space */
+  MR_SPACE_USER = 8,      /* K1 counts |I_u ∩ I_v| per test-user batch, K2 gathers them through the inverted index */
+  MR_SPACE_ITEM = 16,     /* rows of the (weighted) song-song co-occurrence matrices: head rows precomputed once per train set */
+  MR_SPACE_MASK = 24
 };
 
 /* Create a scorer on CUDA device device_ids[0] (n_devices must be 1: one process per GPU).  Replaces nothing in the
@@ -107,13 +112,18 @@ int mr_topk(mr_handle* h, int model, double param, uint64_t seed, int k, int32_t
 /* The same, split for callers that keep results on the device between steps: compute only (results stay in HBM), then fetch. */
 int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k);
 int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int32_t* out_len);
+/* Device addresses of the last mr_topk_device result (int32 [U,k], double [U,k], int32 [U]) for callers that gather it over
+ * NCCL without a host round trip (the reference's `.collect`, DIST:451-478).  Valid until the next call on the handle. */
+int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** len);
 
 /* Introspection used by bench.py / tests. */
-enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5, MR_T_N = 6 };
+enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5,
+       MR_T_PRECOMPUTE = 6, MR_T_HEAD_ROWSUM = 7, MR_T_TAIL_SCATTER = 8, MR_T_N = 9 };
 int mr_get_timing(mr_handle* h, double* ms_out, int n);      /* accumulated CUDA-event ms per phase since the last reset */
 int mr_reset_timing(mr_handle* h);
 int mr_set_profile(mr_handle* h, int on);                   /* toggle MR_PROFILE at run time (it synchronises after every phase) */
-int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated] */
+int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated, space, n_head songs,
+                                                                 test entries on head songs, test entries on tail songs] */
 void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
 
 #ifdef __cplusplus

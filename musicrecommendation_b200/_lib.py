@@ -11,12 +11,13 @@ MR_OK, MR_ERR_PARAM_RANGE, MR_ERR_KEY_MISMATCH, MR_ERR_CUDA, MR_ERR_NCCL, MR_ERR
 MR_UBM, MR_IBM, MR_LC, MR_AGG, MR_STOCH = range(5)
 MR_ENGINE_AUTO, MR_ENGINE_TENSOR, MR_ENGINE_SPARSE = 0, 1, 2
 MR_PROFILE = 4
-TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other"]
+MR_SPACE_AUTO, MR_SPACE_USER, MR_SPACE_ITEM = 0, 8, 16
+TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
 
 # every symbol include/mrscore.h declares
 SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_counts_ubm", "mr_counts_ibm",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_topk", "mr_topk_device",
-           "mr_topk_fetch", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
+           "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
 
 _lib = None
 
@@ -54,6 +55,7 @@ def load():
     lib.mr_topk.argtypes = [vp, i32, dbl, u64, i32, vp, vp, vp]
     lib.mr_topk_device.argtypes = [vp, i32, dbl, u64, i32]
     lib.mr_topk_fetch.argtypes = [vp, i32, vp, vp, vp]
+    lib.mr_topk_device_ptrs.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.mr_get_timing.argtypes = [vp, vp, i32]
     lib.mr_reset_timing.argtypes = [vp]
     lib.mr_set_profile.argtypes = [vp, i32]

@@ -126,26 +126,24 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// ---------------------------------------------------------------- top-k: radix select on the composite key (score, ~song)
-constexpr int kTopkThreads = 512;
-constexpr int kTopkCap = 2048;   // candidate buffer (>= k); bitonic-sorted in shared memory
+// ---------------------------------------------------------------- top-k select
+// One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
+// the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
+//   pass A  max score of the row (and nothing else)
+//   pass B  2048-bin histogram of floor(score * 2047 / max)  — a monotone map, so it is only a pre-filter: the bin that
+//           contains the k-th best key is found, everything in higher bins is certainly in the top-k
+//   pass C  collect every key whose bin >= that bin (usually a few hundred to ~2000 keys) and bitonic-sort them exactly
+// Degenerate rows (huge tie classes such as thousands of exact zeros, or a bin more crowded than the candidate buffer) fall
+// back to an exact most-significant-digit radix select (8-bit digits of the 96-bit key) inside the chosen bin.
+// Every pass streams the row with 4 songs per thread (16-byte loads, 4 independent keys in flight per thread).
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkCap = 2048;    // candidate buffer (>= 2 * k); bitonic-sorted in shared memory
+constexpr int kTopkBins = 2048;
 
 struct KeyCtx {
   int model; double rsu, alpha, oma;
   const long long* su; const long long* si; const double* rsd; const uint64_t* sel;
 };
-
-// Returns false for listened pairs.  Scores are >= 0, so their IEEE bit patterns order like unsigned integers.
-__device__ __forceinline__ bool load_key(const KeyCtx& c, int s, unsigned long long& kb) {
-  long long a = 0, b = 0;
-  if (c.model != MODEL_IBM) { a = c.su[s]; if (a < 0) return false; }
-  if (c.model != MODEL_UBM) { b = c.si[s]; if (b < 0) return false; }
-  bool pick = false;
-  if (c.model >= MODEL_AGG) pick = (c.sel[s >> 6] >> (s & 63)) & 1ULL;
-  const double rds = c.model != MODEL_UBM ? c.rsd[s] : 0.0;
-  kb = static_cast<unsigned long long>(__double_as_longlong(blend_score(c.model, a, b, c.rsu, rds, c.alpha, c.oma, pick)));
-  return true;
-}
 
 // digit d (0 = most significant) of the 96-bit composite (kb : 64, ~song : 32), 8 bits each
 __device__ __forceinline__ uint32_t key_digit(unsigned long long kb, uint32_t inv_song, int d) {
@@ -161,8 +159,57 @@ __device__ __forceinline__ int prefix_cmp(unsigned long long kb, uint32_t inv, u
   }
   if (kb != phi) return kb < phi ? -1 : 1;
   const int sh = 32 - 8 * (nd - 8);
-  const uint32_t a = sh == 32 ? 0u : inv >> sh, b = sh == 32 ? 0u : plo >> sh;
+  const uint32_t a = inv >> sh, b = plo >> sh;
   return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+// Stream the row: f(song, key bits, valid) is called for 4 songs per thread per iteration, the same number of times by every
+// thread of the CTA (so f may use warp collectives); valid is false for listened pairs and past the end of the row.
+template <class F>
+__device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f) {
+  for (int base = 0; base < n_songs; base += 4 * kTopkThreads) {
+    const int s = base + 4 * static_cast<int>(threadIdx.x);
+    long long a[4] = {-1, -1, -1, -1}, b[4] = {-1, -1, -1, -1};
+    double rd[4] = {0, 0, 0, 0};
+    uint64_t selw = 0;
+    if (s < n_songs) {   // rows are padded to a multiple of 32 songs, so the 4-wide loads stay inside the row
+      if (c.model != MODEL_IBM) {
+        const longlong2 x = *reinterpret_cast<const longlong2*>(c.su + s), y = *reinterpret_cast<const longlong2*>(c.su + s + 2);
+        a[0] = x.x; a[1] = x.y; a[2] = y.x; a[3] = y.y;
+      }
+      if (c.model != MODEL_UBM) {
+        const longlong2 x = *reinterpret_cast<const longlong2*>(c.si + s), y = *reinterpret_cast<const longlong2*>(c.si + s + 2);
+        b[0] = x.x; b[1] = x.y; b[2] = y.x; b[3] = y.y;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rd[t] = s + t < n_songs ? c.rsd[s + t] : 0.0;
+      }
+      if (c.model >= MODEL_AGG) selw = c.sel[s >> 6] >> (s & 63);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      bool ok = s + t < n_songs;
+      if (c.model != MODEL_IBM) ok = ok && a[t] >= 0;
+      if (c.model != MODEL_UBM) ok = ok && b[t] >= 0;
+      unsigned long long kb = 0;
+      if (ok) kb = static_cast<unsigned long long>(__double_as_longlong(
+                  blend_score(c.model, a[t], b[t], c.rsu, rd[t], c.alpha, c.oma, (selw >> t) & 1ULL)));
+      f(s + t, kb, ok);
+    }
+  }
+}
+
+// warp-aggregated shared-memory histogram increment: peel the two most common bins of the warp with ballots
+__device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool ok, int lane) {
+  uint32_t pending = __ballot_sync(0xffffffffu, ok);
+#pragma unroll 1
+  for (int round = 0; round < 2 && pending; ++round) {
+    const int leader = __ffs(pending) - 1;
+    const uint32_t lb = __shfl_sync(0xffffffffu, bin, leader);
+    const uint32_t same = __ballot_sync(0xffffffffu, ok && bin == lb) & pending;
+    if (lane == leader) atomicAdd(&hist[lb], __popc(same));
+    pending &= ~same;
+  }
+  if ((pending >> lane) & 1u) atomicAdd(&hist[bin], 1);
 }
 
 __global__ void __launch_bounds__(kTopkThreads)
@@ -172,87 +219,113 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
             int* __restrict__ out_len) {
   __shared__ unsigned long long s_key[kTopkCap];
   __shared__ int s_song[kTopkCap];
-  __shared__ int s_hist[256];
+  __shared__ int s_hist[kTopkBins];
+  __shared__ unsigned long long s_max[kTopkThreads / 32];
   __shared__ int s_count;
-  __shared__ int s_ctl[4];     // 0: chosen digit, 1: items strictly above the prefix bin, 2: bin count, 3: need
+  __shared__ int s_ctl[4];     // 0: chosen bin / digit, 1: keys strictly above it, 2: keys in it, 3: need
 
   const int b = blockIdx.x;
   const int u = u0 + b;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   KeyCtx c;
   c.model = bp.model; c.rsu = rsa[u]; c.alpha = bp.alpha; c.oma = bp.one_minus_alpha;
   c.su = sint_u ? sint_u + static_cast<long long>(b) * spitch : nullptr;
   c.si = sint_i ? sint_i + static_cast<long long>(b) * spitch : nullptr;
   c.rsd = rsd;
   c.sel = sel ? sel + static_cast<long long>(b) * sel_pitch_words : nullptr;
-
-  unsigned long long phi = 0; uint32_t plo = 0;   // selected prefix digits
-  int nd = 0, above = 0, need = 0;
-  for (;;) {
-    for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0;
-    __syncthreads();
-    for (int s0 = 0; s0 < n_songs; s0 += kTopkThreads) {
-      const int s = s0 + tid;
-      unsigned long long kb = 0; bool ok = false;
-      if (s < n_songs) ok = load_key(c, s, kb);
-      const uint32_t inv = ~static_cast<uint32_t>(s);
-      ok = ok && prefix_cmp(kb, inv, phi, plo, nd) == 0;
-      const uint32_t dg = ok ? key_digit(kb, inv, nd) : 0xffffffffu;
-      // warp-aggregated histogram: peel the two most common digits of the warp with ballots, rest with plain atomics
-      uint32_t pending = __ballot_sync(0xffffffffu, ok);
-#pragma unroll 1
-      for (int round = 0; round < 2 && pending; ++round) {
-        const int leader = __ffs(pending) - 1;
-        const uint32_t ld = __shfl_sync(0xffffffffu, dg, leader);
-        const uint32_t same = __ballot_sync(0xffffffffu, dg == ld) & pending;
-        if (lane == leader) atomicAdd(&s_hist[ld], __popc(same));
-        pending &= ~same;
-      }
-      if ((pending >> lane) & 1u) atomicAdd(&s_hist[dg], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (nd == 0) {
-        int total = 0;
-        for (int i = 0; i < 256; ++i) total += s_hist[i];
-        s_ctl[3] = min(k, total);
-      }
-      const int want = s_ctl[3] - above;   // still needed from this prefix
-      int cum = 0, chosen = 0;
-      for (int d = 255; d >= 0; --d) {
-        if (cum + s_hist[d] >= want) { chosen = d; break; }
-        cum += s_hist[d];
-      }
-      s_ctl[0] = chosen; s_ctl[1] = above + cum; s_ctl[2] = s_hist[chosen];
-    }
-    __syncthreads();
-    need = s_ctl[3];
-    if (need == 0) break;
-    const int chosen = s_ctl[0];
-    above = s_ctl[1];
-    if (nd < 8) phi |= static_cast<unsigned long long>(chosen) << (56 - 8 * nd);
-    else plo |= static_cast<uint32_t>(chosen) << (24 - 8 * (nd - 8));
-    ++nd;
-    if (above + s_ctl[2] <= kTopkCap || nd == 12) break;
-    __syncthreads();
-  }
-
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
+
+  // ---- pass A: row maximum
+  unsigned long long mx = 0;
+  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
+  if (lane == 0) s_max[warp] = mx;
+  for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+  __syncthreads();
+  mx = 0;
+  for (int i = 0; i < kTopkThreads / 32; ++i) mx = s_max[i] > mx ? s_max[i] : mx;
+  const double max_score = __longlong_as_double(static_cast<long long>(mx));
+  const double scale = max_score > 0.0 ? __ddiv_rn(static_cast<double>(kTopkBins - 1), max_score) : 0.0;
+  auto bin_of = [&](unsigned long long kb) -> uint32_t {
+    const int d = __double2int_rz(__dmul_rn(__longlong_as_double(static_cast<long long>(kb)), scale));
+    return static_cast<uint32_t>(d > kTopkBins - 1 ? kTopkBins - 1 : d);
+  };
+
+  // ---- pass B: histogram of the monotone bin map
+  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); });
+  __syncthreads();
+  if (warp == 0) {   // find the bin holding the k-th best key: 64 bins per lane, suffix sums across lanes
+    int part = 0;
+    for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
+    int total = part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    int above_lane = 0;   // keys in bins owned by higher lanes
+    for (int l = 0; l < 32; ++l) { const int p = __shfl_sync(0xffffffffu, part, l); if (l > lane) above_lane += p; }
+    const int need = min(k, total);
+    const bool mine = need > 0 && above_lane < need && above_lane + part >= need;
+    if (mine) {
+      int cum = above_lane, chosen = lane * (kTopkBins / 32);
+      for (int i = kTopkBins / 32 - 1; i >= 0; --i) {
+        const int bin = lane * (kTopkBins / 32) + i;
+        if (cum + s_hist[bin] >= need) { chosen = bin; break; }
+        cum += s_hist[bin];
+      }
+      s_ctl[0] = chosen; s_ctl[1] = cum; s_ctl[2] = s_hist[chosen];
+    }
+    if (lane == 0) s_ctl[3] = need;
+  }
+  __syncthreads();
+  const int need = s_ctl[3];
   if (need == 0) {
     for (int i = tid; i < k; i += kTopkThreads) { o_song[i] = -1; o_score[i] = 0.0; }
     if (tid == 0) out_len[u] = 0;
     return;
   }
+  const uint32_t cbin = static_cast<uint32_t>(s_ctl[0]);
+  int above = s_ctl[1];                 // keys strictly better than everything still undecided
+  unsigned long long phi = 0; uint32_t plo = 0; int nd = 0;
+  if (above + s_ctl[2] > kTopkCap) {
+    // ---- degenerate row: exact radix select of the (need - above) best keys inside bin cbin
+    for (;;) {
+      __syncthreads();
+      for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0;
+      __syncthreads();
+      scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
+        const uint32_t inv = ~static_cast<uint32_t>(s);
+        ok = ok && bin_of(kb) == cbin && prefix_cmp(kb, inv, phi, plo, nd) == 0;
+        hist_add(s_hist, ok ? key_digit(kb, inv, nd) : 0u, ok, lane);
+      });
+      __syncthreads();
+      if (tid == 0) {
+        const int want = need - above;
+        int cum = 0, chosen = 0;
+        for (int d = 255; d >= 0; --d) {
+          if (cum + s_hist[d] >= want) { chosen = d; break; }
+          cum += s_hist[d];
+        }
+        s_ctl[0] = chosen; s_ctl[1] = above + cum; s_ctl[2] = s_hist[chosen];
+      }
+      __syncthreads();
+      const int chosen = s_ctl[0];
+      above = s_ctl[1];
+      if (nd < 8) phi |= static_cast<unsigned long long>(chosen) << (56 - 8 * nd);
+      else plo |= static_cast<uint32_t>(chosen) << (24 - 8 * (nd - 8));
+      ++nd;
+      if (above + s_ctl[2] <= kTopkCap || nd == 12) break;
+    }
+  }
 
-  // collect every key whose first nd digits are >= the prefix (count = above + bin <= kTopkCap)
+  // ---- pass C: collect every key in a higher bin, plus the keys of bin cbin at or above the radix prefix
   if (tid == 0) s_count = 0;
   __syncthreads();
-  for (int s0 = 0; s0 < n_songs; s0 += kTopkThreads) {
-    const int s = s0 + tid;
-    unsigned long long kb = 0; bool ok = false;
-    if (s < n_songs) ok = load_key(c, s, kb);
-    ok = ok && prefix_cmp(kb, ~static_cast<uint32_t>(s), phi, plo, nd) >= 0;
+  scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
+    if (ok) {
+      const uint32_t bn = bin_of(kb);
+      ok = bn > cbin || (bn == cbin && prefix_cmp(kb, ~static_cast<uint32_t>(s), phi, plo, nd) >= 0);
+    }
     const uint32_t m = __ballot_sync(0xffffffffu, ok);
     if (m) {
       int base = 0;
@@ -263,7 +336,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
         if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
       }
     }
-  }
+  });
   __syncthreads();
   const int n_cand = min(s_count, kTopkCap);
   int n_sort = 1;

@@ -1,0 +1,160 @@
+// k4_itemspace.cu — the item-space engine: both models as rows of (weighted) song-song co-occurrence matrices.
+//
+//   IBM  Sint_i[u][s] = sum_{j in I_u, j != s} qd[j] * G[j][s]      G[j][s]  = |U_j ∩ U_s| over train users   (MusicRecommender.scala:232-235, 249-257)
+//   UBM  Sint_u[u][s] = sum_{j in I_u}         Gq[j][s]             Gq[j][s] = sum_{v in U_j ∩ U_s} qv[v]      (MusicRecommender.scala:142-148, 159-166:
+//        sum_v |I_u ∩ I_v| qv[v] [s in I_v] regrouped by the shared song j — the same integers, summed in another order)
+//
+// Popular ("head") songs are shared by many test users, so their rows G[j][:], Gq[j][:] are computed once per train set
+// (gram_head_* below, or the tcgen05 count GEMM for dense-friendly shapes) and kept in HBM as dense rows; a test user's score
+// row is then a sum of |I_u ∩ head| coalesced, streaming row reads (head_rowsum_kernel — HBM-bandwidth bound).  The long tail
+// of rarely heard songs is expanded on the fly through the inverted index with exact 64-bit integer atomics
+// (tail_scatter_kernel).  Every entry is an exact integer, so the result equals the user-space engine and the oracle bit for bit.
+#include "mr_common.cuh"
+#include "mr_kernels.h"
+
+namespace mr {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Precompute of the head rows from the inverted index: one warp per (head song h, listener v of that song), lanes over I_v.
+//   G[h][s] += 1, Gq[h][s] += qv[v]   for every s in I_v
+// Work is the flattened list of (h, listener) pairs (lst_ptr = exclusive prefix of the head songs' train degrees) so that
+// the 80k-listener rows and the 400-listener rows balance.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int n_head,
+                         const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
+                         const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
+                         uint32_t* __restrict__ g, unsigned long long* __restrict__ gq, long long pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long n_work = lst_ptr[n_head];
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work; w += n_warps) {
+    int lo = 0, hi = n_head;                       // h = upper_bound(lst_ptr, w) - 1
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (lst_ptr[m + 1] <= w) lo = m + 1; else hi = m; }
+    const int h = lo;
+    const int j = head_song[h];
+    const int v = csc_idx[csc_ptr[j] + (w - lst_ptr[h])];
+    const unsigned long long q = qv[v];
+    const long long b = tr_ptr[v], e = tr_ptr[v + 1];
+    for (long long m = b + lane; m < e; m += 32) {
+      const int s = __ldg(tr_col + m);
+      atomicAdd(g + static_cast<long long>(h) * pitch + s, 1u);
+      atomicAdd(gq + static_cast<long long>(h) * pitch + s, q);
+    }
+  }
+}
+
+int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int n_head, const long long* csc_ptr, const int* csc_idx,
+                             const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
+                             long long pitch, int num_sms, cudaStream_t st) {
+  if (n_head <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(g, 0, static_cast<size_t>(n_head) * pitch * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gq, 0, static_cast<size_t>(n_head) * pitch * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return -1;
+  gram_head_scatter_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, n_head, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Head part of a batch: Sint[b][s] = sum over the user's head entries of the precomputed rows.  Thread = (user b, 2 songs);
+// every row read is a coalesced 8-byte (G) / 16-byte (Gq) vector load along the song axis; 4 rows are kept in flight.
+// kModels: 1 = UBM only, 2 = IBM only, 3 = both.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kModels>
+__global__ void __launch_bounds__(256)
+head_rowsum_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
+                   const uint32_t* __restrict__ hu_q, int u0, const uint32_t* __restrict__ g, const unsigned long long* __restrict__ gq,
+                   long long pitch, int n_songs, long long* __restrict__ sint_u, long long* __restrict__ sint_i, long long spitch) {
+  const int b = blockIdx.y;
+  const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
+  const int s = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (s >= n_songs) return;
+  unsigned long long u0a = 0, u1a = 0, i0a = 0, i1a = 0;
+  long long i = beg;
+  for (; i + 4 <= end; i += 4) {
+    ulonglong2 cu[4]; uint2 ci[4]; uint32_t q[4]; int js[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const long long row = static_cast<long long>(__ldg(hu_row + i + t)) * pitch + s;
+      if (kModels & 1) cu[t] = __ldg(reinterpret_cast<const ulonglong2*>(gq + row));
+      if (kModels & 2) { ci[t] = __ldg(reinterpret_cast<const uint2*>(g + row)); q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (kModels & 1) { u0a += cu[t].x; u1a += cu[t].y; }
+      if (kModels & 2) {
+        if (js[t] != s) i0a += static_cast<unsigned long long>(ci[t].x) * q[t];          // s2 != song, MR:252
+        if (js[t] != s + 1) i1a += static_cast<unsigned long long>(ci[t].y) * q[t];
+      }
+    }
+  }
+  for (; i < end; ++i) {
+    const long long row = static_cast<long long>(__ldg(hu_row + i)) * pitch + s;
+    if (kModels & 1) { const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(gq + row)); u0a += c.x; u1a += c.y; }
+    if (kModels & 2) {
+      const uint2 c = __ldg(reinterpret_cast<const uint2*>(g + row));
+      const uint32_t q = __ldg(hu_q + i); const int j = __ldg(hu_song + i);
+      if (j != s) i0a += static_cast<unsigned long long>(c.x) * q;
+      if (j != s + 1) i1a += static_cast<unsigned long long>(c.y) * q;
+    }
+  }
+  const long long o = static_cast<long long>(b) * spitch + s;
+  if (kModels & 1) *reinterpret_cast<ulonglong2*>(sint_u + o) = make_ulonglong2(u0a, u1a);
+  if (kModels & 2) *reinterpret_cast<ulonglong2*>(sint_i + o) = make_ulonglong2(i0a, i1a);
+}
+
+int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
+                       int n_users, const uint32_t* g, const unsigned long long* gq, long long pitch, int n_songs, long long* sint_u,
+                       long long* sint_i, long long spitch, cudaStream_t st) {
+  if (n_users <= 0 || n_songs <= 0) return 0;
+  const dim3 grid((n_songs + 511) / 512, n_users);
+  if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
+  else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
+  else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tail part of a batch: for every (user b, visible tail song j): for v in U_j^train, for s in I_v, s != j:
+//   Sint_u[b][s] += qv[v],  Sint_i[b][s] += qd[j]
+// One CTA per (b, j) entry; warps stride over the listeners of j, lanes over I_v; exact u64 atomics (fire-and-forget).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kModels>
+__global__ void __launch_bounds__(128)
+tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_song, long long e0, const long long* __restrict__ csc_ptr,
+                    const int* __restrict__ csc_idx, const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col,
+                    const uint32_t* __restrict__ qv, const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u,
+                    long long* __restrict__ sint_i, long long spitch) {
+  const long long e = e0 + blockIdx.x;
+  const int b = tu_user[e] - u0;
+  const int j = tu_song[e];
+  const unsigned long long qj = qd[j];
+  const long long lb = csc_ptr[j], le = csc_ptr[j + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
+  unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
+  for (long long l = lb + warp; l < le; l += n_warps) {
+    const int v = csc_idx[l];
+    const unsigned long long q = qv[v];
+    const long long rb = tr_ptr[v], re = tr_ptr[v + 1];
+    for (long long m = rb + lane; m < re; m += 32) {
+      const int s = __ldg(tr_col + m);
+      if (s == j) continue;
+      if (kModels & 1) atomicAdd(su + s, q);
+      if (kModels & 2) atomicAdd(si + s, qj);
+    }
+  }
+}
+
+int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, long long e0, long long n_entries, const long long* csc_ptr,
+                        const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv, const uint32_t* qd, int u0,
+                        long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st) {
+  if (n_entries <= 0) return 0;
+  const int grid = static_cast<int>(n_entries);
+  if (models == 1) tail_scatter_kernel<1><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else if (models == 2) tail_scatter_kernel<2><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else tail_scatter_kernel<3><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mr

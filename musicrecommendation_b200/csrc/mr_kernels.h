@@ -51,6 +51,17 @@ int launch_aggregate_w32(const AggItems& items, const int* csc_idx, const uint32
 int launch_aggregate_ibm(const long long* te_ptr, const int* te_col, const int* te_grow, const uint32_t* qd, int u0, int n_users,
                          const int32_t* g, long long ldg, int n_songs, long long* sint, long long spitch, cudaStream_t st);
 
+// ---- item-space engine (k4_itemspace.cu)
+int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int n_head, const long long* csc_ptr, const int* csc_idx,
+                             const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
+                             long long pitch, int num_sms, cudaStream_t st);
+int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
+                       int n_users, const uint32_t* g, const unsigned long long* gq, long long pitch, int n_songs, long long* sint_u,
+                       long long* sint_i, long long spitch, cudaStream_t st);
+int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, long long e0, long long n_entries, const long long* csc_ptr,
+                        const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv, const uint32_t* qd, int u0,
+                        long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st);
+
 // ---- K3 (k3_topk.cu)
 int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
                          long long spitch, cudaStream_t st);

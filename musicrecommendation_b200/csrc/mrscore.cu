@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,9 +46,18 @@ struct mr_handle {
   int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
   long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
   uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
+  // item-space engine: head songs and their precomputed rows
+  int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false;
+  std::vector<int> head_index;         // song -> head row or -1
+  int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint32_t* d_g_head = nullptr; unsigned long long* d_gq_head = nullptr;
+  long long *d_hu_ptr = nullptr; int *d_hu_row = nullptr, *d_hu_song = nullptr; uint32_t* d_hu_q = nullptr;
+  int *d_tu_user = nullptr, *d_tu_song = nullptr; std::vector<long long> h_tu_ptr; long long n_head_entries = 0, n_tail_entries = 0;
   // test shard (freed / reallocated by mr_set_test_users)
   int U = 0; long long nnz_te = 0; bool have_test = false;
-  std::vector<void*> test_allocs;
+  // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
+  enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
+         SL_TU_SONG, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+  void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
   std::vector<long long> batch_row_off; int* d_rows = nullptr; int max_batch_rows = 0;
@@ -61,7 +71,7 @@ struct mr_handle {
   // results
   int *d_out_song = nullptr, *d_out_len = nullptr; double* d_out_score = nullptr; int out_k = 0; bool have_topk = false;
   // profiling
-  cudaEvent_t ev[2] = {nullptr, nullptr}; double t_ms[MR_T_N] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[2] = {nullptr, nullptr}; double t_ms[MR_T_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -99,6 +109,28 @@ int dev_alloc(mr_handle* h, Tp** out, size_t count, std::vector<void*>& owner) {
   owner.push_back(p);
   h->dev_bytes += bytes;
   *out = static_cast<Tp*>(p);
+  return MR_OK;
+}
+
+template <class Tp>
+int slot_alloc(mr_handle* h, int slot, Tp** out, size_t count) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+  if (h->slot_cap[slot] < bytes) {
+    if (h->slot_p[slot]) { cudaFree(h->slot_p[slot]); h->dev_bytes -= h->slot_cap[slot]; h->slot_p[slot] = nullptr; h->slot_cap[slot] = 0; }
+    const size_t cap = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    MR_CUDA(h, cudaMalloc(&p, cap));
+    h->slot_p[slot] = p; h->slot_cap[slot] = cap; h->dev_bytes += cap;
+  }
+  *out = static_cast<Tp*>(h->slot_p[slot]);
+  return MR_OK;
+}
+
+template <class Tp>
+int slot_upload(mr_handle* h, int slot, Tp** out, const Tp* src, size_t count) {
+  int rc = slot_alloc(h, slot, out, count);
+  if (rc) return rc;
+  if (count) MR_CUDA(h, cudaMemcpyAsync(*out, src, count * sizeof(Tp), cudaMemcpyHostToDevice, h->stream));
   return MR_OK;
 }
 
@@ -233,14 +265,41 @@ int ensure_gram_ws(mr_handle* h, int n_rows) {
   return MR_OK;
 }
 
+// Item-space: compute the dense rows G[h][:], Gq[h][:] of the head songs once per train set (lazily, on first use).
+int ensure_head_rows(mr_handle* h) {
+  if (h->head_ready) return MR_OK;
+  int rc;
+  const size_t n = static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch;
+  if ((rc = dev_alloc(h, &h->d_g_head, n, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_gq_head, n, h->allocs))) return rc;
+  PhaseTimer t(h, MR_T_PRECOMPUTE);
+  MR_LAUNCH(h, launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, h->n_head, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                        h->d_qv, h->d_g_head, h->d_gq_head, h->spitch, h->num_sms, h->stream));
+  h->head_ready = true;
+  return MR_OK;
+}
+
 enum RunMode { RUN_TOPK, RUN_DENSE, RUN_COUNTS_UBM, RUN_SIM_UBM };
 
 int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode mode, void* host_out) {
   const bool need_ubm = model != MODEL_IBM;
   const bool need_ibm = model != MODEL_UBM && mode != RUN_COUNTS_UBM && mode != RUN_SIM_UBM;
+  const bool item_space = h->space == MR_SPACE_ITEM && (mode == RUN_TOPK || mode == RUN_DENSE);
+  if (item_space) { int rc = ensure_head_rows(h); if (rc) return rc; }
   for (int b0 = 0; b0 < h->U; b0 += kUserBatch) {
     const int nb = std::min(kUserBatch, h->U - b0);
-    if (need_ubm) {
+    if (item_space) {
+      const int models = (need_ubm ? 1 : 0) | (need_ibm ? 2 : 0);
+      {
+        PhaseTimer t(h, MR_T_HEAD_ROWSUM);
+        MR_LAUNCH(h, launch_head_rowsum(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_g_head, h->d_gq_head, h->spitch,
+                                        h->S, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+      }
+      PhaseTimer t(h, MR_T_TAIL_SCATTER);
+      const long long e0 = h->h_tu_ptr[b0], e1 = h->h_tu_ptr[b0 + nb];
+      MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, e0, e1 - e0, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                       h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+    } else if (need_ubm) {
       int rc = count_ubm_batch(h, b0, nb);
       if (rc) return rc;
       if (mode == RUN_COUNTS_UBM || mode == RUN_SIM_UBM) {
@@ -264,7 +323,9 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       AggItems items{h->d_item_song, h->d_item_begin, h->d_item_len, h->d_item_split, h->n_items};
       MR_LAUNCH(h, launch_aggregate_ubm(items, h->d_csc_idx, h->d_qv, h->d_ct, h->T, h->d_sint_u, h->spitch, h->num_sms, h->stream));
     }
-    if (need_ibm && h->engine == MR_ENGINE_SPARSE) {
+    if (item_space) {
+      // both models were produced above
+    } else if (need_ibm && h->engine == MR_ENGINE_SPARSE) {
       // user-space formulation: weighted intersection counts, then the same inverted-index gather as UBM
       CarryList carry{h->d_carry_count, h->d_carry_events, h->carry_cap};
       {
@@ -306,7 +367,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
                                h->d_rsd, k, h->d_out_song, h->d_out_score, h->d_out_len, h->stream));
     }
   }
-  if (need_ibm && h->engine == MR_ENGINE_SPARSE) {
+  if (need_ibm && !item_space && h->engine == MR_ENGINE_SPARSE) {
     // the carry list of the u32 weighted-count panel must not have overflowed (it never does on real data: an event needs
     // more than ~64 songs shared between one test user and one train user)
     MR_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -358,6 +419,7 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
   h->num_sms = prop.multiProcessorCount;
   h->flags = flags;
   h->engine = flags & MR_ENGINE_MASK;
+  h->space_flag = flags & MR_SPACE_MASK;
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   MR_CUDA(h, cudaEventCreate(&h->ev[0]));
   MR_CUDA(h, cudaEventCreate(&h->ev[1]));
@@ -367,7 +429,7 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
 void mr_destroy(mr_handle* h) {
   if (!h) return;
   if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
-  free_list(h->test_allocs);
+  for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);
   free_list(h->allocs);
   if (h->h_carry_seen) cudaFreeHost(h->h_carry_seen);
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
@@ -471,6 +533,28 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
   h->sel_pitch = (S + 63) / 64;
   if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kUserBatch) * h->sel_pitch, h->allocs))) return rc;
+  // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
+  {
+    long long min_deg = std::max<long long>(2, S / 1000);
+    if (const char* e = getenv("MRSCORE_HEAD_MIN_DEG")) min_deg = std::max(1LL, atoll(e));
+    size_t free_b = 0, total_b = 0;
+    MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    const long long max_rows = static_cast<long long>((free_b / 2) / (static_cast<size_t>(h->spitch) * 12));
+    std::vector<int> order(S);
+    for (int s = 0; s < S; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return csc_ptr[a + 1] - csc_ptr[a] > csc_ptr[b + 1] - csc_ptr[b]; });
+    h->head_index.assign(S, -1);
+    std::vector<int> head_song; std::vector<long long> lst_ptr(1, 0);
+    for (int r = 0; r < S && r < max_rows; ++r) {
+      const int s = order[r]; const long long d = csc_ptr[s + 1] - csc_ptr[s];
+      if (d < min_deg) break;
+      h->head_index[s] = static_cast<int>(head_song.size());
+      head_song.push_back(s); lst_ptr.push_back(lst_ptr.back() + d);
+    }
+    h->n_head = static_cast<int>(head_song.size());
+    if ((rc = dev_upload(h, &h->d_head_song, head_song.data(), head_song.size(), h->allocs))) return rc;
+    if ((rc = dev_upload(h, &h->d_head_lst_ptr, lst_ptr.data(), lst_ptr.size(), h->allocs))) return rc;
+  }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->loaded = true;
   if (n_test > 0) return mr_set_test_users(h, n_test, te_rowptr, te_col, deg_test, 0, 0);
@@ -487,10 +571,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     if (te_rowptr[u + 1] - te_rowptr[u] > 65535) return fail(h, MR_ERR_BAD_ARG, "test user %d has more than 65535 visible songs (u16 count panel)", u);
   MR_CUDA(h, cudaSetDevice(h->device));
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
-  for (void* p : h->test_allocs) { cudaFree(p); }
-  h->test_allocs.clear();
   h->have_test = false; h->have_topk = false; h->out_k = 0;
-  h->d_out_song = nullptr; h->d_out_score = nullptr; h->d_out_len = nullptr; h->d_dense = nullptr; h->d_cnt = nullptr; h->d_simf = nullptr;
   const int U = n_test; const long long nnz = te_rowptr[U];
   h->U = U; h->nnz_te = nnz;
   h->h_te_ptr.assign(te_rowptr, te_rowptr + U + 1);
@@ -519,13 +600,35 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     h->batch_row_off[b + 1] = static_cast<long long>(rows_all.size());
     h->max_batch_rows = std::max<int>(h->max_batch_rows, static_cast<int>(uni.size()));
   }
-  if ((rc = dev_upload(h, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size(), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_rsa, rsa.data(), rsa.size(), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_rsa_f, rsaf.data(), rsaf.size(), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_pair_base, pair_base.data(), pair_base.size(), h->test_allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_rows, rows_all.data(), rows_all.size(), h->test_allocs))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_TE_PTR, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_TE_COL, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz)))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_TE_GROW, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz)))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_RSA, &h->d_rsa, rsa.data(), rsa.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_RSA_F, &h->d_rsa_f, rsaf.data(), rsaf.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_PAIR_BASE, &h->d_pair_base, pair_base.data(), pair_base.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_ROWS, &h->d_rows, rows_all.data(), rows_all.size()))) return rc;
+  {  // item-space work lists: per user the precomputed head rows it sums, and its tail songs expanded on the fly
+    std::vector<long long> hu_ptr(static_cast<size_t>(U) + 1, 0);
+    std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q;
+    h->h_tu_ptr.assign(static_cast<size_t>(U) + 1, 0);
+    for (int u = 0; u < U; ++u) {
+      for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) {
+        const int j = te_col[e]; const int hr = h->head_index[j];
+        if (hr >= 0) { hu_row.push_back(hr); hu_song.push_back(j); hu_q.push_back(q_of(h->deg_song[j], kQScaleIbm)); }
+        else { tu_user.push_back(u); tu_song.push_back(j); }
+      }
+      hu_ptr[u + 1] = static_cast<long long>(hu_row.size());
+      h->h_tu_ptr[u + 1] = static_cast<long long>(tu_user.size());
+    }
+    if ((rc = slot_upload(h, mr_handle::SL_HU_PTR, &h->d_hu_ptr, hu_ptr.data(), hu_ptr.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_HU_ROW, &h->d_hu_row, hu_row.data(), hu_row.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_HU_SONG, &h->d_hu_song, hu_song.data(), hu_song.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_HU_Q, &h->d_hu_q, hu_q.data(), hu_q.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_TU_USER, &h->d_tu_user, tu_user.data(), tu_user.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_TU_SONG, &h->d_tu_song, tu_song.data(), tu_song.size()))) return rc;
+    h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
+    h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
+  }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_test = true;
   return MR_OK;
@@ -543,7 +646,7 @@ int mr_counts_ubm(mr_handle* h, int32_t* out_UxT) {
   int rc = require_test(h);
   if (rc) return rc;
   if (!out_UxT) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if (!h->d_cnt && (rc = dev_alloc(h, &h->d_cnt, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_CNT, &h->d_cnt, static_cast<size_t>(kUserBatch) * h->T))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp);
   return run_batches(h, MODEL_UBM, bp, 0, RUN_COUNTS_UBM, out_UxT);
 }
@@ -554,7 +657,7 @@ int mr_similarity_ubm(mr_handle* h, float* out_UxT) {
   if (!out_UxT) return fail(h, MR_ERR_BAD_ARG, "null output");
   if (h->engine == MR_ENGINE_TENSOR) {
     // cosine normalisation fused into the GEMM epilogue: out[b][v] = c / (sqrt|I_u| * sqrt|I_v|)   (MR:147-148)
-    if (!h->d_simf && (rc = dev_alloc(h, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+    if ((rc = slot_alloc(h, mr_handle::SL_SIMF, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T))) return rc;
     for (int b0 = 0; b0 < h->U; b0 += kUserBatch) {
       const int nb = std::min(kUserBatch, h->U - b0);
       MR_LAUNCH(h, launch_expand_rows(h->d_te_ptr, h->d_te_col, nullptr, b0, nb, kUserBatch, h->pitchS, h->d_Ate, h->stream));
@@ -566,7 +669,7 @@ int mr_similarity_ubm(mr_handle* h, float* out_UxT) {
     }
     return MR_OK;
   }
-  if (!h->d_simf && (rc = dev_alloc(h, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T, h->test_allocs))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_SIMF, &h->d_simf, static_cast<size_t>(kUserBatch) * h->T))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp);
   return run_batches(h, MODEL_UBM, bp, 0, RUN_SIM_UBM, out_UxT);
 }
@@ -619,7 +722,7 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if (!h->d_dense && (rc = dev_alloc(h, &h->d_dense, static_cast<size_t>(kUserBatch) * h->S, h->test_allocs))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(kUserBatch) * h->S))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
   return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
@@ -660,12 +763,10 @@ int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) 
   BlendParams bp;
   if ((rc = make_blend_params(h, model, param, seed, h->n_pairs_total, &bp))) return rc;
   bp.pair_base = h->d_pair_base;
-  if (h->out_k != k) {
-    if ((rc = dev_alloc(h, &h->d_out_song, static_cast<size_t>(h->U) * k, h->test_allocs))) return rc;
-    if ((rc = dev_alloc(h, &h->d_out_score, static_cast<size_t>(h->U) * k, h->test_allocs))) return rc;
-    if ((rc = dev_alloc(h, &h->d_out_len, static_cast<size_t>(h->U), h->test_allocs))) return rc;
-    h->out_k = k;
-  }
+  if ((rc = slot_alloc(h, mr_handle::SL_OUT_SONG, &h->d_out_song, static_cast<size_t>(h->U) * k))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_OUT_SCORE, &h->d_out_score, static_cast<size_t>(h->U) * k))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_OUT_LEN, &h->d_out_len, static_cast<size_t>(h->U)))) return rc;
+  h->out_k = k;
   if (model != MR_UBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   h->have_topk = false;
   if ((rc = run_batches(h, model, bp, k, RUN_TOPK, nullptr))) return rc;
@@ -682,6 +783,16 @@ int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int
   MR_CUDA(h, cudaMemcpyAsync(out_score, h->d_out_score, static_cast<size_t>(h->U) * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   MR_CUDA(h, cudaMemcpyAsync(out_len, h->d_out_len, static_cast<size_t>(h->U) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MR_OK;
+}
+
+int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** len) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (!h->have_topk || h->out_k != k) return fail(h, MR_ERR_STATE, "no top-%d result on the device (call mr_topk_device first)", k);
+  if (song) *song = h->d_out_song;
+  if (score) *score = h->d_out_score;
+  if (len) *len = h->d_out_len;
   return MR_OK;
 }
 
@@ -703,8 +814,9 @@ int mr_reset_timing(mr_handle* h) {
 }
 int mr_get_info(mr_handle* h, int64_t* out, int n) {
   if (!h || !out) return MR_ERR_BAD_ARG;
-  const int64_t v[6] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes)};
-  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  const int64_t v[10] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
+                         h->n_head_entries, h->n_tail_entries};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
   return MR_OK;
 }
 int mr_set_profile(mr_handle* h, int on) {

@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing: one process per GPU, test users sharded, no data-path collective.
+
+The reference distributes the same way (distributed.scala:450-452: `ctx.parallelize(testUsers, slices).map(getRanks1).collect`):
+every worker holds the whole train set (there: the task closure; here: a train replica in each GPU's HBM) and scores a
+contiguous range of test users.  Scored pairs are independent, so the only exchange is the `collect` — here an all-gather of the
+fixed-size top-k blocks (k * 12 bytes per test user) over NCCL.  The index-dependent blends (Aggregation MR:372-382, Stochastic
+MR:447) need each shard's position in the global (user, song)-sorted pair list; `pair_index_bases` computes it from the CSR alone.
+
+Works with any torch.distributed backend: `nccl` with CUDA tensors on the GPU box, `gloo` with CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .dataset import Dataset
+
+
+def shard_range(n_users: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced test-user range of `rank` (first n_users % world ranks get one extra user)."""
+    base, rem = divmod(n_users, world)
+    u0 = rank * base + min(rank, rem)
+    return u0, u0 + base + (1 if rank < rem else 0)
+
+
+def pair_index_bases(ds: Dataset, world: int) -> tuple[np.ndarray, int]:
+    """(index of each rank's first scored pair in the global MAIN:57-59 order, total number of scored pairs)."""
+    per_user = ds.S - np.diff(ds.te_ptr)                       # unlistened songs per test user (MR:109)
+    prefix = np.concatenate([[0], np.cumsum(per_user)])
+    starts = np.array([prefix[shard_range(ds.U, r, world)[0]] for r in range(world)], np.int64)
+    return starts, int(prefix[-1])
+
+
+def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, group=None):
+    """All-gather the per-shard top-k blocks into the full [U, k] result (the reference's `.collect`).  Accepts numpy arrays or
+    torch tensors (CPU for gloo, CUDA for nccl); returns torch tensors on the same device."""
+    import torch
+    import torch.distributed as dist
+    song = torch.as_tensor(song)
+    score = torch.as_tensor(score)
+    length = torch.as_tensor(length)
+    if world == 1:
+        return song, score, length
+    k = song.shape[1]
+    sizes = [shard_range(n_users_total, r, world) for r in range(world)]
+    max_n = max(b - a for a, b in sizes)
+
+    def pad(t, fill):
+        if t.shape[0] == max_n:
+            return t.contiguous()
+        extra = torch.full((max_n - t.shape[0],) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+        return torch.cat([t, extra]).contiguous()
+
+    outs = []
+    for t, fill in ((song, -1), (score, 0.0), (length, 0)):
+        p = pad(t, fill)
+        buf = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(buf, p, group=group)
+        outs.append(torch.cat([b[: hi - lo] for b, (lo, hi) in zip(buf, sizes)]))
+    return tuple(outs)

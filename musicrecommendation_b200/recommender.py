@@ -121,7 +121,7 @@ class MusicRecommender:
     """`new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12).  Also accepts a ready `Dataset`."""
 
     def __init__(self, trainFile, testFile=None, testLabelsFile=None, device: int = 0, engine: int = _lib.MR_ENGINE_AUTO,
-                 profile: bool = False):
+                 profile: bool = False, space: int = _lib.MR_SPACE_AUTO):
         if isinstance(trainFile, Dataset):
             ds = trainFile
         else:
@@ -132,7 +132,7 @@ class MusicRecommender:
         self._lib = _lib.load()
         self._h = C.c_void_p()
         dev = (C.c_int * 1)(device)
-        rc = self._lib.mr_create(C.byref(self._h), dev, 1, engine | (_lib.MR_PROFILE if profile else 0))
+        rc = self._lib.mr_create(C.byref(self._h), dev, 1, engine | space | (_lib.MR_PROFILE if profile else 0))
         self._check(rc)
         a = self._arrs = dict(
             tr_ptr=np.ascontiguousarray(ds.tr_ptr, np.int64), tr_col=np.ascontiguousarray(ds.tr_col, np.int32),
@@ -239,6 +239,19 @@ class MusicRecommender:
         self._check(self._lib.mr_topk(self._h, model, float(param), C.c_uint64(seed & (2**64 - 1)), k, _p(song), _p(score), _p(ln)))
         return song, score, ln
 
+    def topk_device_tensors(self, k: int):
+        """torch views (no copy) of the last mr_topk_device result in this GPU's HBM: (song int32 [U,k], score f64 [U,k], len int32 [U])."""
+        import torch
+        ps, pv, pl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.mr_topk_device_ptrs(self._h, k, C.byref(ps), C.byref(pv), C.byref(pl)))
+        U = self.ds.U
+
+        class _Arr:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+        return (torch.as_tensor(_Arr(ps.value, (U, k), "<i4"), device="cuda"), torch.as_tensor(_Arr(pv.value, (U, k), "<f8"), device="cuda"),
+                torch.as_tensor(_Arr(pl.value, (U,), "<i4"), device="cuda"))
+
     # ------------------------------------------------------------------ parity probes / similarity products
     def counts_ubm(self) -> np.ndarray:
         out = np.empty((self.ds.U, self.ds.T), np.int32)
@@ -261,16 +274,17 @@ class MusicRecommender:
         return out
 
     def timing(self, reset: bool = False) -> dict:
-        t = (C.c_double * 6)()
-        self._lib.mr_get_timing(self._h, t, 6)
+        t = (C.c_double * 9)()
+        self._lib.mr_get_timing(self._h, t, 9)
         if reset:
             self._lib.mr_reset_timing(self._h)
         return dict(zip(_lib.TIMING_NAMES, list(t)))
 
     def info(self) -> dict:
-        v = (C.c_int64 * 6)()
-        self._lib.mr_get_info(self._h, v, 6)
-        return dict(zip(["engine", "launches", "dense_bytes", "n_items", "num_sms", "device_bytes"], list(v)))
+        v = (C.c_int64 * 10)()
+        self._lib.mr_get_info(self._h, v, 10)
+        return dict(zip(["engine", "launches", "dense_bytes", "n_items", "num_sms", "device_bytes", "space", "n_head", "head_entries",
+                         "tail_entries"], list(v)))
 
     # ------------------------------------------------------------------ model file I/O (MR:489-512)
     def writeModelOnFile(self, model: Model, outputFileName: str = "") -> None:

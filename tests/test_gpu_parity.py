@@ -12,7 +12,9 @@ from musicrecommendation_b200.dataset import fixture_4_3, synth, synth_config
 from musicrecommendation_b200.recommender import MusicRecommender, ParameterRange, KeyMismatch, Model, evaluate_map
 
 GOLD = Path(__file__).resolve().parent / "golden"
-ENGINES = [_lib.MR_ENGINE_TENSOR, _lib.MR_ENGINE_SPARSE]
+# count engine x scoring formulation: every combination must give the oracle's bits
+ENGINES = [dict(engine=_lib.MR_ENGINE_TENSOR, space=_lib.MR_SPACE_USER), dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_USER),
+           dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM)]
 KINDS = {"ubm": _lib.MR_UBM, "ibm": _lib.MR_IBM}
 
 
@@ -28,7 +30,7 @@ def assert_bits_equal(a, b):
     np.testing.assert_array_equal(np.where(np.isnan(a), 0, a).view(np.int64), np.where(np.isnan(b), 0, b).view(np.int64))
 
 
-@pytest.fixture(scope="module", params=ENGINES, ids=["tensor", "sparse"])
+@pytest.fixture(scope="module", params=ENGINES, ids=["tensor-userspace", "sparse-userspace", "itemspace"])
 def engine(request, mrlib):
     return request.param
 
@@ -36,7 +38,7 @@ def engine(request, mrlib):
 def test_fixture_4_3(engine, oracle_lib):
     fx = json.loads((GOLD / "fixture_4_3.json").read_text())
     ds = fixture_4_3()
-    with MusicRecommender(ds, engine=engine) as mr:
+    with MusicRecommender(ds, **engine) as mr:
         assert mr.counts_ubm().tolist() == [fx["ubm_counts"]["X"], fx["ubm_counts"]["Y"]]
         g = mr.counts_ibm(0, 4)
         assert g[0, 1] == 1 and g[1, 2] == 1 and g[0, 2] == 0 and g[1, 1] == 2
@@ -58,7 +60,7 @@ def test_fixture_4_3(engine, oracle_lib):
 
 
 def check_dataset(ds, oracle_lib, engine, k=500, blends=True):
-    with MusicRecommender(ds, engine=engine) as mr:
+    with MusicRecommender(ds, **engine) as mr:
         # K1: intersection counts, bit-exact
         np.testing.assert_array_equal(mr.counts_ubm(), oracle_lib.counts_ubm(ds))
         rows = np.unique(np.concatenate([[0, ds.S - 1], np.random.default_rng(0).integers(0, ds.S, 30)])).astype(np.int32)
@@ -102,7 +104,7 @@ def test_golden_small_seed11(engine, oracle_lib):
     """The committed golden vectors (as-written restatement) against the CUDA path."""
     g = np.load(GOLD / "small_seed11.npz")
     ds = synth(T=40, U=6, S=500, seed=11)
-    with MusicRecommender(ds, engine=engine) as mr:
+    with MusicRecommender(ds, **engine) as mr:
         np.testing.assert_array_equal(mr.counts_ubm(), g["counts_ubm"])
         np.testing.assert_array_equal(mr.counts_ibm(0, 64), g["gram_0_64"])
         ubm, ibm = mr.getUserBasedModel(), mr.getItemBasedModel()
@@ -132,15 +134,15 @@ def test_popular_songs_split_across_warps(engine, oracle_lib):
 def test_config_c1(engine, oracle_lib):
     ds = synth_config("c1")
     info = check_dataset(ds, oracle_lib, engine)
-    assert info["engine"] == engine
+    assert info["engine"] == engine["engine"] and info["space"] == engine["space"]
 
 
 def test_config_c2_and_c3_topk(oracle_lib):
     """BASELINE.json configs[1] and configs[2] shapes on the default (auto) engine: rankings and blends bit-exact."""
     for name in ("c2", "c3"):
         ds = synth_config(name)
-        info = check_dataset(ds, oracle_lib, _lib.MR_ENGINE_AUTO, blends=(name == "c3"))
-        assert info["engine"] == _lib.MR_ENGINE_TENSOR
+        info = check_dataset(ds, oracle_lib, dict(engine=_lib.MR_ENGINE_AUTO), blends=(name == "c3"))
+        assert info["engine"] == _lib.MR_ENGINE_TENSOR and info["space"] == _lib.MR_SPACE_USER
 
 
 def test_edge_cases(engine, oracle_lib):
@@ -153,7 +155,7 @@ def test_edge_cases(engine, oracle_lib):
     lab = (np.arange(U), np.array([3, 4, 5, 6, 7]))
     from musicrecommendation_b200.dataset import from_triplets
     ds = from_triplets(tr, te, lab, T, U, S)
-    with MusicRecommender(ds, engine=engine) as mr:
+    with MusicRecommender(ds, **engine) as mr:
         ubm = mr.getUserBasedModel()
         assert_bits_equal(ubm.scores, oracle_lib.canon_scores(ds, oracle_lib.UBM))
         assert np.all(compact(ubm.scores[1]) == 0.0) and np.all(compact(ubm.scores[3]) == 0.0)
@@ -198,7 +200,7 @@ def test_error_behaviour(mrlib, oracle_lib):
 def test_similarity_products(engine, oracle_lib):
     """Cosine normalisation fused into the count-GEMM epilogue (fp32 products): user-user MR:140-149, item-item MR:230-239."""
     ds = synth(T=300, U=20, S=2000, seed=1)
-    with MusicRecommender(ds, engine=engine) as mr:
+    with MusicRecommender(ds, **engine) as mr:
         c = oracle_lib.counts_ubm(ds).astype(np.float64)
         want = c / (np.sqrt(ds.deg_te.astype(np.float64))[:, None] * np.sqrt(ds.deg_tr.astype(np.float64))[None, :])
         np.testing.assert_allclose(mr.similarity_ubm(), want, rtol=1e-5, atol=0)
