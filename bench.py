@@ -267,8 +267,9 @@ def main():
     torch.cuda.synchronize()
     phases = mr.timing()
     lib.mr_set_profile(h, 0)
-    n_batches = (U + 127) // 128
     info = mr.info()
+    batch = 296 if info["space"] == _lib.MR_SPACE_ITEM else 128     # kItemBatch / kUserBatch
+    n_batches = (U + batch - 1) // batch
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")

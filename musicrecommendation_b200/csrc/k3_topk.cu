@@ -129,7 +129,7 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 // ---------------------------------------------------------------- top-k select
 // One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
 // the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
-//   pass A  max score of the row (and nothing else)
+//   pass A  (sampled) max score of the row — only fixes the scale of the bin map
 //   pass B  2048-bin histogram of floor(score * 2047 / max)  — a monotone map, so it is only a pre-filter: the bin that
 //           contains the k-th best key is found, everything in higher bins is certainly in the top-k
 //   pass C  collect every key whose bin >= that bin (usually a few hundred to ~2000 keys) and bitonic-sort them exactly
@@ -166,8 +166,8 @@ __device__ __forceinline__ int prefix_cmp(unsigned long long kb, uint32_t inv, u
 // Stream the row: f(song, key bits, valid) is called for 4 songs per thread per iteration, the same number of times by every
 // thread of the CTA (so f may use warp collectives); valid is false for listened pairs and past the end of the row.
 template <class F>
-__device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f) {
-  for (int base = 0; base < n_songs; base += 4 * kTopkThreads) {
+__device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f, int chunk_stride = 1) {
+  for (int base = 0; base < n_songs; base += 4 * kTopkThreads * chunk_stride) {
     const int s = base + 4 * static_cast<int>(threadIdx.x);
     long long a[4] = {-1, -1, -1, -1}, b[4] = {-1, -1, -1, -1};
     double rd[4] = {0, 0, 0, 0};
@@ -236,9 +236,10 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
 
-  // ---- pass A: row maximum
+  // ---- pass A: (sampled) row maximum.  Any scale keeps the bin map monotone — scores above a too-small estimate simply share
+  // the top bin — so long rows look at every 8th 4096-song chunk only; the estimate just has to be close to the true maximum.
   unsigned long long mx = 0;
-  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; });
+  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; }, n_songs > 65536 ? 8 : 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
   if (lane == 0) s_max[warp] = mx;

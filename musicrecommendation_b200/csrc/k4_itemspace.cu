@@ -117,25 +117,30 @@ int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, c
 // ---------------------------------------------------------------------------------------------------------------------
 // Tail part of a batch: for every (user b, visible tail song j): for v in U_j^train, for s in I_v, s != j:
 //   Sint_u[b][s] += qv[v],  Sint_i[b][s] += qd[j]
-// One CTA per (b, j) entry; warps stride over the listeners of j, lanes over I_v; exact u64 atomics (fire-and-forget).
+// Work is the flattened list of (tail entry, listener) pairs (tu_lptr = exclusive prefix of the entries' train degrees): one
+// warp per pair, lanes over I_v, exact u64 atomics (fire-and-forget).  Flattening keeps all 64 warp slots of every SM busy
+// although entries have between 1 and a few hundred listeners.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int kModels>
-__global__ void __launch_bounds__(128)
-tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_song, long long e0, const long long* __restrict__ csc_ptr,
-                    const int* __restrict__ csc_idx, const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col,
-                    const uint32_t* __restrict__ qv, const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u,
-                    long long* __restrict__ sint_i, long long spitch) {
-  const long long e = e0 + blockIdx.x;
-  const int b = tu_user[e] - u0;
-  const int j = tu_song[e];
-  const unsigned long long qj = qd[j];
-  const long long lb = csc_ptr[j], le = csc_ptr[j + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
-  unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
-  for (long long l = lb + warp; l < le; l += n_warps) {
-    const int v = csc_idx[l];
-    const unsigned long long q = qv[v];
+__global__ void __launch_bounds__(256)
+tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_song, const long long* __restrict__ tu_lptr,
+                    long long e0, long long e1, const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
+                    const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
+                    const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u, long long* __restrict__ sint_i,
+                    long long spitch) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = tu_lptr[e0], w1 = tu_lptr[e1];
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long w = w0 + static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < w1; w += n_warps) {
+    long long lo = e0, hi = e1;                      // e = upper_bound(tu_lptr, w) - 1 within [e0, e1)
+    while (lo < hi) { const long long m = (lo + hi) >> 1; if (tu_lptr[m + 1] <= w) lo = m + 1; else hi = m; }
+    const long long e = lo;
+    const int b = tu_user[e] - u0;
+    const int j = tu_song[e];
+    const int v = csc_idx[csc_ptr[j] + (w - tu_lptr[e])];
+    const unsigned long long q = qv[v], qj = qd[j];
+    unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
+    unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
     const long long rb = tr_ptr[v], re = tr_ptr[v + 1];
     for (long long m = rb + lane; m < re; m += 32) {
       const int s = __ldg(tr_col + m);
@@ -146,14 +151,14 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
   }
 }
 
-int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, long long e0, long long n_entries, const long long* csc_ptr,
-                        const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv, const uint32_t* qd, int u0,
-                        long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st) {
-  if (n_entries <= 0) return 0;
-  const int grid = static_cast<int>(n_entries);
-  if (models == 1) tail_scatter_kernel<1><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else if (models == 2) tail_scatter_kernel<2><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else tail_scatter_kernel<3><<<grid, 128, 0, st>>>(tu_user, tu_song, e0, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
+                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
+                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, int num_sms, cudaStream_t st) {
+  if (e1 <= e0) return 0;
+  const int grid = num_sms * 8;
+  if (models == 1) tail_scatter_kernel<1><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else if (models == 2) tail_scatter_kernel<2><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else tail_scatter_kernel<3><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -5,7 +5,8 @@
 
 namespace mr {
 
-constexpr int kUserBatch = 128;   // test users per batch = UMMA M
+constexpr int kUserBatch = 128;   // test users per batch of the user-space engine = UMMA M
+constexpr int kItemBatch = 296;   // test users per batch of the item-space engine = 2 top-k CTAs per SM on 148 SMs
 // Count panels K1 hands to K2, train-user-major so that one gathered row serves the whole 128-user batch in one coalesced read:
 //   UBM  u16 Ct[T][128]   256-byte rows     IBM (user space)  u32 Wi[T][128]   512-byte rows
 // (A sub-panel-major variant with 32-byte, L2-resident rows was measured 1.7-1.9x slower on B200: random 32-byte sector
@@ -58,9 +59,9 @@ int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int
 int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
                        int n_users, const uint32_t* g, const unsigned long long* gq, long long pitch, int n_songs, long long* sint_u,
                        long long* sint_i, long long spitch, cudaStream_t st);
-int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, long long e0, long long n_entries, const long long* csc_ptr,
-                        const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv, const uint32_t* qd, int u0,
-                        long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st);
+int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
+                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
+                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, int num_sms, cudaStream_t st);
 
 // ---- K3 (k3_topk.cu)
 int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,

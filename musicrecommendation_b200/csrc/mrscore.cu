@@ -42,7 +42,7 @@ struct mr_handle {
   int T = 0, S = 0; long long nnz_tr = 0; bool loaded = false;
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr;
-  std::vector<int32_t> deg_song;
+  std::vector<int32_t> deg_song, deg_song_train;
   int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
   long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
   uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
@@ -51,12 +51,12 @@ struct mr_handle {
   std::vector<int> head_index;         // song -> head row or -1
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint32_t* d_g_head = nullptr; unsigned long long* d_gq_head = nullptr;
   long long *d_hu_ptr = nullptr; int *d_hu_row = nullptr, *d_hu_song = nullptr; uint32_t* d_hu_q = nullptr;
-  int *d_tu_user = nullptr, *d_tu_song = nullptr; std::vector<long long> h_tu_ptr; long long n_head_entries = 0, n_tail_entries = 0;
+  int *d_tu_user = nullptr, *d_tu_song = nullptr; long long* d_tu_lptr = nullptr; std::vector<long long> h_tu_ptr; long long n_head_entries = 0, n_tail_entries = 0;
   // test shard (freed / reallocated by mr_set_test_users)
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -286,8 +286,9 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
   const bool need_ibm = model != MODEL_UBM && mode != RUN_COUNTS_UBM && mode != RUN_SIM_UBM;
   const bool item_space = h->space == MR_SPACE_ITEM && (mode == RUN_TOPK || mode == RUN_DENSE);
   if (item_space) { int rc = ensure_head_rows(h); if (rc) return rc; }
-  for (int b0 = 0; b0 < h->U; b0 += kUserBatch) {
-    const int nb = std::min(kUserBatch, h->U - b0);
+  const int batch = item_space ? kItemBatch : kUserBatch;
+  for (int b0 = 0; b0 < h->U; b0 += batch) {
+    const int nb = std::min(batch, h->U - b0);
     if (item_space) {
       const int models = (need_ubm ? 1 : 0) | (need_ibm ? 2 : 0);
       {
@@ -297,8 +298,8 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       }
       PhaseTimer t(h, MR_T_TAIL_SCATTER);
       const long long e0 = h->h_tu_ptr[b0], e1 = h->h_tu_ptr[b0 + nb];
-      MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, e0, e1 - e0, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                       h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+      MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
+                                       h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->num_sms, h->stream));
     } else if (need_ubm) {
       int rc = count_ubm_batch(h, b0, nb);
       if (rc) return rc;
@@ -339,9 +340,9 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       MR_LAUNCH(h, launch_carry_fixup(carry, h->d_tr_ptr, h->d_tr_col, h->d_sint_i, h->spitch, h->stream));
       MR_CUDA(h, cudaMemcpyAsync(h->h_carry_seen + (b0 / kUserBatch) % 4096, h->d_carry_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     } else if (need_ibm) {
-      const int batch = b0 / kUserBatch;
-      const long long r_off = h->batch_row_off[batch];
-      const int n_rows = static_cast<int>(h->batch_row_off[batch + 1] - r_off);
+      const int bi = b0 / kUserBatch;
+      const long long r_off = h->batch_row_off[bi];
+      const int n_rows = static_cast<int>(h->batch_row_off[bi + 1] - r_off);
       if (n_rows > 0) {
         int rc = gram_rows(h, h->d_rows + r_off, n_rows);
         if (rc) return rc;
@@ -455,6 +456,8 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   h->pitchS = round_up(S, 128); h->pitchT = round_up(T, 128);
   h->spitch = round_up(S, 32); h->ldg = round_up(S, 32);
   h->deg_song.assign(deg_song_all, deg_song_all + S);
+  h->deg_song_train.assign(S, 0);
+  for (long long i = 0; i < nnz; ++i) h->deg_song_train[tr_col[i]]++;
 
   // inverted index (counting sort; listeners of a song ascending because rows are visited in order)
   std::vector<long long> csc_ptr(static_cast<size_t>(S) + 1, 0);
@@ -529,10 +532,10 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_carry_seen), 4096 * sizeof(unsigned int)));
     memset(h->h_carry_seen, 0, 4096 * sizeof(unsigned int));
   }
-  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
-  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kUserBatch) * h->spitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(kItemBatch) * h->spitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kItemBatch) * h->spitch, h->allocs))) return rc;
   h->sel_pitch = (S + 63) / 64;
-  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kUserBatch) * h->sel_pitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kItemBatch) * h->sel_pitch, h->allocs))) return rc;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
     long long min_deg = std::max<long long>(2, S / 1000);
@@ -609,13 +612,13 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   if ((rc = slot_upload(h, mr_handle::SL_ROWS, &h->d_rows, rows_all.data(), rows_all.size()))) return rc;
   {  // item-space work lists: per user the precomputed head rows it sums, and its tail songs expanded on the fly
     std::vector<long long> hu_ptr(static_cast<size_t>(U) + 1, 0);
-    std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q;
+    std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q; std::vector<long long> tu_lptr(1, 0);
     h->h_tu_ptr.assign(static_cast<size_t>(U) + 1, 0);
     for (int u = 0; u < U; ++u) {
       for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) {
         const int j = te_col[e]; const int hr = h->head_index[j];
         if (hr >= 0) { hu_row.push_back(hr); hu_song.push_back(j); hu_q.push_back(q_of(h->deg_song[j], kQScaleIbm)); }
-        else { tu_user.push_back(u); tu_song.push_back(j); }
+        else { tu_user.push_back(u); tu_song.push_back(j); tu_lptr.push_back(tu_lptr.back() + h->deg_song_train[j]); }
       }
       hu_ptr[u + 1] = static_cast<long long>(hu_row.size());
       h->h_tu_ptr[u + 1] = static_cast<long long>(tu_user.size());
@@ -626,6 +629,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     if ((rc = slot_upload(h, mr_handle::SL_HU_Q, &h->d_hu_q, hu_q.data(), hu_q.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_TU_USER, &h->d_tu_user, tu_user.data(), tu_user.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_TU_SONG, &h->d_tu_song, tu_song.data(), tu_song.size()))) return rc;
+    if ((rc = slot_upload(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, tu_lptr.data(), tu_lptr.size()))) return rc;
     h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
   }
@@ -722,7 +726,7 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(kUserBatch) * h->S))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(kItemBatch) * h->S))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
   return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
