@@ -85,6 +85,10 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs,
 int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const int32_t* te_col, const int32_t* deg_test,
                       int64_t pair_index_base, int64_t n_pairs_total);
 
+/* Build the item-space head rows (G, Gq of the popular songs) now instead of lazily on the first scoring call
+ * that uses them.  One-off per train set: tensor-core GEMMs on the tensor engine, inverted-index scatter otherwise. */
+int mr_prepare(mr_handle* h);
+
 /* Parity probes for kernel K1: out[u*T + v] = |I_u ∩ I_v| (numerator of MR:142-145), and rows [s0,s1) of the train
  * co-occurrence matrix out[(i-s0)*S + j] = |U_i ∩ U_j| over train users (numerator of MR:232-235). */
 int mr_counts_ubm(mr_handle* h, int32_t* out_UxT);

@@ -15,6 +15,7 @@
 //   EPI_I32      int32 C row-major                      (parity probes mr_counts_*, Gram rows consumed by the IBM aggregation)
 //   EPI_U16_T    uint16 C^T  (Ct[n][m], m contiguous)   (UBM: train-user-major count panel consumed by the K2 gather)
 //   EPI_COS_F32  float   C[m][n] / (sqrt(da[m]) * sqrt(db[n]))   fused cosine normalisation (similarity products, MR:147-148 / 237-238)
+//   EPI_ACC_U64  u64 out (+)= C << shift                         byte-plane accumulation of the weighted Gram Gq (item-space head rows)
 #include "mr_common.cuh"
 #include "mr_kernels.h"
 
@@ -46,6 +47,8 @@ struct GemmParams {
   long long ld;        // leading dimension of `out` in elements
   const float* rsa;    // EPI_COS_F32: 1/sqrt(deg) per A row, per B row (0 where deg == 0)
   const float* rsb;
+  int shift;           // EPI_ACC_U64: out = (plane 0 ? 0 : out) + (u64(acc) << shift)  (byte-plane weighted Gram)
+  int accumulate;
 };
 
 template <int BN, int EPI>
@@ -165,6 +168,23 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.N) dst[j * kUserBatch] = static_cast<uint16_t>(r[j] > 65535u ? 65535u : r[j]);
           }
+        } else if constexpr (EPI == EPI_ACC_U64) {
+          // byte-plane accumulation of a weighted contraction: the B operand held byte `shift/8` of a 32-bit weight
+          if (m < p.M) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.out) + static_cast<long long>(m) * p.ld + n0;
+            if (n0 + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                ulonglong2 v = p.accumulate ? *reinterpret_cast<ulonglong2*>(dst + j) : make_ulonglong2(0, 0);
+                v.x += static_cast<unsigned long long>(r[j]) << p.shift;
+                v.y += static_cast<unsigned long long>(r[j + 1]) << p.shift;
+                *reinterpret_cast<ulonglong2*>(dst + j) = v;
+              }
+            } else {
+              for (int j = 0; j < 32 && n0 + j < p.N; ++j)
+                dst[j] = (p.accumulate ? dst[j] : 0ULL) + (static_cast<unsigned long long>(r[j]) << p.shift);
+            }
+          }
         } else {  // EPI_COS_F32
           if (m < p.M) {
             const float ra = p.rsa[m];
@@ -205,6 +225,26 @@ __global__ void expand_rows_kernel(const long long* __restrict__ ptr, const int*
       const int rid = rows ? rows[r] : row0 + static_cast<int>(r);
       const long long b = ptr[rid], e = ptr[rid + 1];
       for (long long i = b + lane; i < e; i += 32) dst[idx[i]] = 1;
+    }
+  }
+}
+
+// Weighted variant for the byte-plane GEMMs: out[r][col] = byte `plane` of weight[col] (instead of 1).
+__global__ void expand_rows_weighted_kernel(const long long* __restrict__ ptr, const int* __restrict__ idx,
+                                            const uint32_t* __restrict__ weight, int plane, int n_rows, long long pitch,
+                                            uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); r < n_rows;
+       r += static_cast<long long>(gridDim.x) * warps_per_block) {
+    uint8_t* dst = out + r * pitch;
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (long long i = lane; i < pitch / 16; i += 32) d4[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const long long b = ptr[r], e = ptr[r + 1];
+    for (long long i = b + lane; i < e; i += 32) {
+      const int c = idx[i];
+      dst[c] = static_cast<uint8_t>((weight[c] >> (8 * plane)) & 255u);
     }
   }
 }
@@ -257,7 +297,8 @@ static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 int launch_count_gemm(const uint8_t* A, long long a_rows, const uint8_t* B, long long b_rows, long long pitch, int M, int N,
-                      int epi, void* out, long long ld, const float* rsa, const float* rsb, int num_sms, cudaStream_t st) {
+                      int epi, void* out, long long ld, const float* rsa, const float* rsb, int num_sms, cudaStream_t st,
+                      int shift, int accumulate) {
   if (pitch % kBK != 0 || M <= 0 || N <= 0) return -3;
   const int bn = (N > 128) ? 256 : 128;
   CUtensorMap ta, tb;
@@ -270,15 +311,17 @@ int launch_count_gemm(const uint8_t* A, long long a_rows, const uint8_t* B, long
   p.num_k_blocks = static_cast<int>(pitch / kBK);
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;
-  p.out = out; p.ld = ld; p.rsa = rsa; p.rsb = rsb;
+  p.out = out; p.ld = ld; p.rsa = rsa; p.rsb = rsb; p.shift = shift; p.accumulate = accumulate;
   cudaError_t e;
   if (bn == 256) {
     e = epi == EPI_I32 ? launch_gemm_t<256, EPI_I32>(ta, tb, p, num_sms, st)
       : epi == EPI_U16_T ? launch_gemm_t<256, EPI_U16_T>(ta, tb, p, num_sms, st)
+      : epi == EPI_ACC_U64 ? launch_gemm_t<256, EPI_ACC_U64>(ta, tb, p, num_sms, st)
                          : launch_gemm_t<256, EPI_COS_F32>(ta, tb, p, num_sms, st);
   } else {
     e = epi == EPI_I32 ? launch_gemm_t<128, EPI_I32>(ta, tb, p, num_sms, st)
       : epi == EPI_U16_T ? launch_gemm_t<128, EPI_U16_T>(ta, tb, p, num_sms, st)
+      : epi == EPI_ACC_U64 ? launch_gemm_t<128, EPI_ACC_U64>(ta, tb, p, num_sms, st)
                          : launch_gemm_t<128, EPI_COS_F32>(ta, tb, p, num_sms, st);
   }
   return e == cudaSuccess ? 0 : -100 - static_cast<int>(e);
@@ -291,6 +334,16 @@ int launch_expand_rows(const long long* ptr, const int* idx, const int* rows, in
   long long blocks = (static_cast<long long>(n_rows_pad) + wpb - 1) / wpb;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   expand_rows_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(ptr, idx, rows, row0, n_rows, n_rows_pad, pitch, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_expand_rows_weighted(const long long* ptr, const int* idx, const uint32_t* weight, int plane, int n_rows, long long pitch,
+                                uint8_t* out, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  const int threads = 256, wpb = threads / 32;
+  long long blocks = (static_cast<long long>(n_rows) + wpb - 1) / wpb;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  expand_rows_weighted_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(ptr, idx, weight, plane, n_rows, pitch, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -272,9 +272,46 @@ int ensure_head_rows(mr_handle* h) {
   const size_t n = static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch;
   if ((rc = dev_alloc(h, &h->d_g_head, n, h->allocs))) return rc;
   if ((rc = dev_alloc(h, &h->d_gq_head, n, h->allocs))) return rc;
-  PhaseTimer t(h, MR_T_PRECOMPUTE);
-  MR_LAUNCH(h, launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, h->n_head, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                        h->d_qv, h->d_g_head, h->d_gq_head, h->spitch, h->num_sms, h->stream));
+  if (h->engine == MR_ENGINE_TENSOR && h->n_head > 0 && h->T < (1 << 23)) {
+    // Head rows on the tensor cores: G = A_head · A_trT^T as one 0/1 count GEMM, and the weighted Gram Gq as four byte-plane
+    // GEMMs (B operand = byte k of q_31(|I_v|) at the train-user columns; 255 * T < 2^31 keeps every plane exact in int32).
+    const int chunk = 4096;
+    uint8_t *a_rows = nullptr, *b_plane = nullptr;
+    std::vector<void*> tmp;
+    if ((rc = dev_alloc(h, &a_rows, static_cast<size_t>(chunk) * h->pitchT, tmp))) { free_list(tmp); return rc; }
+    if ((rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT, tmp))) { free_list(tmp); return rc; }
+    for (int plane = -1; plane < 4; ++plane) {
+      const uint8_t* b_op = h->d_AtrT;
+      if (plane >= 0) {
+        PhaseTimer t(h, MR_T_EXPAND);
+        MR_LAUNCH(h, launch_expand_rows_weighted(h->d_csc_ptr, h->d_csc_idx, h->d_qv, plane, h->S, h->pitchT, b_plane, h->stream));
+        b_op = b_plane;
+      }
+      for (int r0 = 0; r0 < h->n_head; r0 += chunk) {
+        const int n = std::min(chunk, h->n_head - r0);
+        const int n_pad = static_cast<int>(round_up(n, 128));
+        {
+          PhaseTimer t(h, MR_T_EXPAND);
+          MR_LAUNCH(h, launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, h->d_head_song + r0, 0, n, n_pad, h->pitchT, a_rows, h->stream));
+        }
+        PhaseTimer t(h, MR_T_COUNT);
+        if (plane < 0)
+          MR_LAUNCH(h, launch_count_gemm(a_rows, n_pad, b_op, h->S, h->pitchT, n, h->S, EPI_I32, h->d_g_head + static_cast<long long>(r0) * h->spitch,
+                                         h->spitch, nullptr, nullptr, h->num_sms, h->stream));
+        else
+          MR_LAUNCH(h, launch_count_gemm(a_rows, n_pad, b_op, h->S, h->pitchT, n, h->S, EPI_ACC_U64,
+                                         h->d_gq_head + static_cast<long long>(r0) * h->spitch, h->spitch, nullptr, nullptr, h->num_sms, h->stream,
+                                         8 * plane, plane > 0));
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    free_list(tmp);
+    if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "tensor-core head-row precompute: %s", cudaGetErrorString(e));
+  } else {
+    PhaseTimer t(h, MR_T_PRECOMPUTE);
+    MR_LAUNCH(h, launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, h->n_head, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                          h->d_qv, h->d_g_head, h->d_gq_head, h->spitch, h->num_sms, h->stream));
+  }
   h->head_ready = true;
   return MR_OK;
 }
@@ -821,6 +858,15 @@ int mr_get_info(mr_handle* h, int64_t* out, int n) {
   const int64_t v[10] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
                          h->n_head_entries, h->n_tail_entries};
   for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  return MR_OK;
+}
+int mr_prepare(mr_handle* h) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  int rc = ensure_head_rows(h);
+  if (rc) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
   return MR_OK;
 }
 int mr_set_profile(mr_handle* h, int on) {

@@ -239,6 +239,10 @@ class MusicRecommender:
         self._check(self._lib.mr_topk(self._h, model, float(param), C.c_uint64(seed & (2**64 - 1)), k, _p(song), _p(score), _p(ln)))
         return song, score, ln
 
+    def prepare(self):
+        """Build the item-space head rows now (one-off per train set) instead of lazily."""
+        self._check(self._lib.mr_prepare(self._h))
+
     def topk_device_tensors(self, k: int):
         """torch views (no copy) of the last mr_topk_device result in this GPU's HBM: (song int32 [U,k], score f64 [U,k], len int32 [U])."""
         import torch

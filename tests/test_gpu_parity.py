@@ -14,7 +14,7 @@ from musicrecommendation_b200.recommender import MusicRecommender, ParameterRang
 GOLD = Path(__file__).resolve().parent / "golden"
 # count engine x scoring formulation: every combination must give the oracle's bits
 ENGINES = [dict(engine=_lib.MR_ENGINE_TENSOR, space=_lib.MR_SPACE_USER), dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_USER),
-           dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM)]
+           dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM), dict(engine=_lib.MR_ENGINE_TENSOR, space=_lib.MR_SPACE_ITEM)]
 KINDS = {"ubm": _lib.MR_UBM, "ibm": _lib.MR_IBM}
 
 
@@ -30,7 +30,7 @@ def assert_bits_equal(a, b):
     np.testing.assert_array_equal(np.where(np.isnan(a), 0, a).view(np.int64), np.where(np.isnan(b), 0, b).view(np.int64))
 
 
-@pytest.fixture(scope="module", params=ENGINES, ids=["tensor-userspace", "sparse-userspace", "itemspace"])
+@pytest.fixture(scope="module", params=ENGINES, ids=["tensor-userspace", "sparse-userspace", "sparse-itemspace", "tensor-itemspace"])
 def engine(request, mrlib):
     return request.param
 
