@@ -118,11 +118,12 @@ def cpu_port_sample(ds, n_users: int, threads: int | None = None):
     sub = ds.shard_test_users(0, n_users)
     t0 = time.perf_counter()
     pairs = 0
+    tops = []
     for m in (oracle.UBM, oracle.IBM):
         sc = oracle.canon_scores(sub, m)
-        oracle.topk(sc, K_TOP)
+        tops.append(oracle.topk(sc, K_TOP))
         pairs += sub.n_pairs
-    return pairs, time.perf_counter() - t0, oracle.num_threads()
+    return pairs, time.perf_counter() - t0, oracle.num_threads(), tops
 
 
 def run_reference(args, rank, world):
@@ -133,7 +134,7 @@ def run_reference(args, rank, world):
     times = []
     pairs = 0
     for i in range(args.warmup + args.steps):
-        p, dt, thr = cpu_port_sample(ds, n_users)
+        p, dt, thr, _ = cpu_port_sample(ds, n_users)
         if i >= args.warmup:
             times.append(dt)
             pairs = p
@@ -333,7 +334,15 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "checksum": checksum,
         }
         if not args.no_cpu_baseline:
-            pairs_c, sec_c, thr = cpu_port_sample(ds, args.ref_users)
+            pairs_c, sec_c, thr, tops = cpu_port_sample(ds, args.ref_users)
+            # full-size parity: the same users' top-500 from the CUDA path must equal the oracle's bit for bit
+            n_chk = min(args.ref_users, U)
+            equal = {}
+            for name, model, (ws, wv, wl) in (("ubm", _lib.MR_UBM, tops[0]), ("ibm", _lib.MR_IBM, tops[1])):
+                gs, gv, gl = mr.getTopK(model, k=k)
+                equal[name] = bool(np.array_equal(gs[:n_chk], ws) and np.array_equal(gv[:n_chk].view(np.int64), wv.view(np.int64))
+                                   and np.array_equal(gl[:n_chk], wl))
+            line["parity"] = {"users_checked": n_chk, "top500_ids_and_scores_bit_equal": equal}
             line["cpu_baseline"] = {"value": pairs_c / sec_c, "unit": "pairs/s", "cores": thr, "kind": "port",
                                     "sample": f"first {min(args.ref_users, U)} test users of rank 0's shard, UBM+IBM canonical CPU port + top-{K_TOP}, {sec_c:.1f}s"}
         print(json.dumps(line), flush=True)

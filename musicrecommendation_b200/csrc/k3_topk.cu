@@ -129,12 +129,14 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 // ---------------------------------------------------------------- top-k select
 // One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
 // the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
-//   pass A  (sampled) max score of the row — only fixes the scale of the bin map
-//   pass B  2048-bin histogram of floor(score * 2047 / max)  — a monotone map, so it is only a pre-filter: the bin that
-//           contains the k-th best key is found, everything in higher bins is certainly in the top-k
-//   pass C  collect every key whose bin >= that bin (usually a few hundred to ~2000 keys) and bitonic-sort them exactly
-// Degenerate rows (huge tie classes such as thousands of exact zeros, or a bin more crowded than the candidate buffer) fall
-// back to an exact most-significant-digit radix select (8-bit digits of the 96-bit key) inside the chosen bin.
+// The monotone map bin(score) = floor(score * 2047 / max) is only ever a PRE-FILTER; exactness comes from the final sort.
+//   long rows (S > 65536):  A1 max and A2 2048-bin histogram over every 8th 4096-song chunk (1/8 of the row each) predict a cut
+//                           bin with ~1.5 k keys above it; ONE full pass collects the keys at or above the cut and counts the valid
+//                           ones; accepted when min(k, valid) <= collected <= 2048, i.e. 1.25 passes over the row in total
+//   otherwise / on reject:  exact path — full histogram, the bin holding the k-th best key, collect pass
+//   degenerate rows (thousands of exact ties such as all-zero rows, or a bin more crowded than the candidate buffer): exact
+//                           most-significant-digit radix select (8-bit digits of the 96-bit key) inside the chosen bin
+// The collected keys (<= 2048) are bitonic-sorted exactly in shared memory: key descending, song ascending.
 // Every pass streams the row with 4 songs per thread (16-byte loads, 4 independent keys in flight per thread).
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkCap = 2048;    // candidate buffer (>= 2 * k); bitonic-sorted in shared memory
@@ -221,7 +223,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   __shared__ int s_song[kTopkCap];
   __shared__ int s_hist[kTopkBins];
   __shared__ unsigned long long s_max[kTopkThreads / 32];
-  __shared__ int s_count;
+  __shared__ int s_count, s_valid;
   __shared__ int s_ctl[4];     // 0: chosen bin / digit, 1: keys strictly above it, 2: keys in it, 3: need
 
   const int b = blockIdx.x;
@@ -236,14 +238,16 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
 
-  // ---- pass A: (sampled) row maximum.  Any scale keeps the bin map monotone — scores above a too-small estimate simply share
-  // the top bin — so long rows look at every 8th 4096-song chunk only; the estimate just has to be close to the true maximum.
+  // ---- pass A1: (sampled) row maximum.  Any scale keeps the bin map monotone — scores above a too-small estimate simply
+  // share the top bin — so long rows look at every 8th 4096-song chunk only.
+  const int stride = n_songs > 65536 ? 8 : 1;
   unsigned long long mx = 0;
-  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; }, n_songs > 65536 ? 8 : 1);
+  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; }, stride);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
   if (lane == 0) s_max[warp] = mx;
   for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+  if (tid == 0) { s_count = 0; s_valid = 0; }
   __syncthreads();
   mx = 0;
   for (int i = 0; i < kTopkThreads / 32; ++i) mx = s_max[i] > mx ? s_max[i] : mx;
@@ -253,91 +257,141 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
     const int d = __double2int_rz(__dmul_rn(__longlong_as_double(static_cast<long long>(kb)), scale));
     return static_cast<uint32_t>(d > kTopkBins - 1 ? kTopkBins - 1 : d);
   };
-
-  // ---- pass B: histogram of the monotone bin map
-  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); });
-  __syncthreads();
-  if (warp == 0) {   // find the bin holding the k-th best key: 64 bins per lane, suffix sums across lanes
-    int part = 0;
-    for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
-    int total = part;
+  // suffix search over the 2048-bin histogram by warp 0: the highest bin such that `want` keys lie in it or above
+  auto find_bin = [&](int want_or_k, bool clamp_to_total) {
+    if (warp == 0) {
+      int part = 0;
+      for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
+      int total = part;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    int above_lane = 0;   // keys in bins owned by higher lanes
-    for (int l = 0; l < 32; ++l) { const int p = __shfl_sync(0xffffffffu, part, l); if (l > lane) above_lane += p; }
-    const int need = min(k, total);
-    const bool mine = need > 0 && above_lane < need && above_lane + part >= need;
-    if (mine) {
-      int cum = above_lane, chosen = lane * (kTopkBins / 32);
-      for (int i = kTopkBins / 32 - 1; i >= 0; --i) {
-        const int bin = lane * (kTopkBins / 32) + i;
-        if (cum + s_hist[bin] >= need) { chosen = bin; break; }
-        cum += s_hist[bin];
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      int above_lane = 0;   // keys in bins owned by higher lanes
+      for (int l = 0; l < 32; ++l) { const int pp = __shfl_sync(0xffffffffu, part, l); if (l > lane) above_lane += pp; }
+      const int want = clamp_to_total ? min(want_or_k, total) : want_or_k;
+      if (lane == 0) { s_ctl[3] = want; if (want > total) { s_ctl[0] = 0; s_ctl[1] = total - s_hist[0]; s_ctl[2] = s_hist[0]; } }
+      const bool mine = want > 0 && above_lane < want && above_lane + part >= want;
+      if (mine) {
+        int cum = above_lane, chosen = lane * (kTopkBins / 32);
+        for (int i = kTopkBins / 32 - 1; i >= 0; --i) {
+          const int bin = lane * (kTopkBins / 32) + i;
+          if (cum + s_hist[bin] >= want) { chosen = bin; break; }
+          cum += s_hist[bin];
+        }
+        s_ctl[0] = chosen; s_ctl[1] = cum; s_ctl[2] = s_hist[chosen];
       }
-      s_ctl[0] = chosen; s_ctl[1] = cum; s_ctl[2] = s_hist[chosen];
     }
-    if (lane == 0) s_ctl[3] = need;
-  }
+  };
+
+  // ---- pass A2: histogram of the monotone bin map over the same (sampled) chunks
+  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); }, stride);
   __syncthreads();
-  const int need = s_ctl[3];
+
+  int need = 0;
+  bool collected = false;
+  uint32_t cbin = 0; unsigned long long phi = 0; uint32_t plo = 0; int nd = 0;
+  if (stride > 1) {
+    // ---- fast path for long rows: the sample predicts a cut bin above which about 1.5 k keys lie; ONE full pass collects every
+    // key at or above it and counts the valid keys.  It is exact whenever at least min(k, valid) and at most kTopkCap keys were
+    // collected (the cut is only a pre-filter); otherwise the exact three-pass path below runs.
+    find_bin((k + k / 2 + 64 + stride - 1) / stride, false);
+    __syncthreads();
+    const uint32_t cut = static_cast<uint32_t>(s_ctl[0]);
+    __syncthreads();
+    int my_valid = 0;
+    scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
+      my_valid += ok;
+      ok = ok && bin_of(kb) >= cut;
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok) {
+          const int pos = base + __popc(m & ((1u << lane) - 1));
+          if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
+        }
+      }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
+    if (lane == 0) atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    need = min(k, s_valid);
+    collected = s_count >= need && s_count <= kTopkCap;
+    __syncthreads();
+    if (!collected) {   // rebuild the exact histogram over the whole row
+      for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); });
+      __syncthreads();
+    }
+  }
+  if (!collected) {
+    // ---- exact path: the bin holding the k-th best key from the full histogram
+    find_bin(k, true);
+    __syncthreads();
+    need = s_ctl[3];
+    if (need > 0) {
+      cbin = static_cast<uint32_t>(s_ctl[0]);
+      int above = s_ctl[1];                 // keys strictly better than everything still undecided
+      if (above + s_ctl[2] > kTopkCap) {
+        // degenerate row: exact radix select of the (need - above) best keys inside bin cbin
+        for (;;) {
+          __syncthreads();
+          for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0;
+          __syncthreads();
+          scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
+            const uint32_t inv = ~static_cast<uint32_t>(s);
+            ok = ok && bin_of(kb) == cbin && prefix_cmp(kb, inv, phi, plo, nd) == 0;
+            hist_add(s_hist, ok ? key_digit(kb, inv, nd) : 0u, ok, lane);
+          });
+          __syncthreads();
+          if (tid == 0) {
+            const int want = need - above;
+            int cum = 0, chosen = 0;
+            for (int d = 255; d >= 0; --d) {
+              if (cum + s_hist[d] >= want) { chosen = d; break; }
+              cum += s_hist[d];
+            }
+            s_ctl[0] = chosen; s_ctl[1] = above + cum; s_ctl[2] = s_hist[chosen];
+          }
+          __syncthreads();
+          const int chosen = s_ctl[0];
+          above = s_ctl[1];
+          if (nd < 8) phi |= static_cast<unsigned long long>(chosen) << (56 - 8 * nd);
+          else plo |= static_cast<uint32_t>(chosen) << (24 - 8 * (nd - 8));
+          ++nd;
+          if (above + s_ctl[2] <= kTopkCap || nd == 12) break;
+        }
+      }
+      // pass C: collect every key in a higher bin, plus the keys of bin cbin at or above the radix prefix
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
+        if (ok) {
+          const uint32_t bn = bin_of(kb);
+          ok = bn > cbin || (bn == cbin && prefix_cmp(kb, ~static_cast<uint32_t>(s), phi, plo, nd) >= 0);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (ok) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
+          }
+        }
+      });
+    }
+  }
   if (need == 0) {
     for (int i = tid; i < k; i += kTopkThreads) { o_song[i] = -1; o_score[i] = 0.0; }
     if (tid == 0) out_len[u] = 0;
     return;
   }
-  const uint32_t cbin = static_cast<uint32_t>(s_ctl[0]);
-  int above = s_ctl[1];                 // keys strictly better than everything still undecided
-  unsigned long long phi = 0; uint32_t plo = 0; int nd = 0;
-  if (above + s_ctl[2] > kTopkCap) {
-    // ---- degenerate row: exact radix select of the (need - above) best keys inside bin cbin
-    for (;;) {
-      __syncthreads();
-      for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0;
-      __syncthreads();
-      scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
-        const uint32_t inv = ~static_cast<uint32_t>(s);
-        ok = ok && bin_of(kb) == cbin && prefix_cmp(kb, inv, phi, plo, nd) == 0;
-        hist_add(s_hist, ok ? key_digit(kb, inv, nd) : 0u, ok, lane);
-      });
-      __syncthreads();
-      if (tid == 0) {
-        const int want = need - above;
-        int cum = 0, chosen = 0;
-        for (int d = 255; d >= 0; --d) {
-          if (cum + s_hist[d] >= want) { chosen = d; break; }
-          cum += s_hist[d];
-        }
-        s_ctl[0] = chosen; s_ctl[1] = above + cum; s_ctl[2] = s_hist[chosen];
-      }
-      __syncthreads();
-      const int chosen = s_ctl[0];
-      above = s_ctl[1];
-      if (nd < 8) phi |= static_cast<unsigned long long>(chosen) << (56 - 8 * nd);
-      else plo |= static_cast<uint32_t>(chosen) << (24 - 8 * (nd - 8));
-      ++nd;
-      if (above + s_ctl[2] <= kTopkCap || nd == 12) break;
-    }
-  }
-
-  // ---- pass C: collect every key in a higher bin, plus the keys of bin cbin at or above the radix prefix
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
-    if (ok) {
-      const uint32_t bn = bin_of(kb);
-      ok = bn > cbin || (bn == cbin && prefix_cmp(kb, ~static_cast<uint32_t>(s), phi, plo, nd) >= 0);
-    }
-    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-    if (m) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (ok) {
-        const int pos = base + __popc(m & ((1u << lane) - 1));
-        if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
-      }
-    }
-  });
   __syncthreads();
   const int n_cand = min(s_count, kTopkCap);
   int n_sort = 1;

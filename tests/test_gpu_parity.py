@@ -131,6 +131,13 @@ def test_popular_songs_split_across_warps(engine, oracle_lib):
     check_dataset(ds, oracle_lib, engine, blends=False)
 
 
+def test_long_rows_take_the_sampled_topk_path(oracle_lib):
+    """Rows longer than 65536 songs use the sampled-cut single-pass select; it must still equal the exact ranking."""
+    ds = synth(T=3000, U=40, S=70000, seed=8)
+    for cfg in (dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM), dict(engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_USER)):
+        check_dataset(ds, oracle_lib, cfg, blends=True)
+
+
 def test_config_c1(engine, oracle_lib):
     ds = synth_config("c1")
     info = check_dataset(ds, oracle_lib, engine)
