@@ -126,6 +126,40 @@ def cpu_port_sample(ds, n_users: int, threads: int | None = None):
     return pairs, time.perf_counter() - t0, oracle.num_threads(), tops
 
 
+def as_written_sample(ds, n_songs_ubm: int = 48, n_songs_ibm: int = 48):
+    """The reference's loops AS WRITTEN (oracle.naive_sample: MusicRecommender.scala:105-307, linear `contains` scans, cosine
+    recomputed per neighbour) with OpenMP over the pair loop (= `.par`, MR:119-125) on a handful of pairs of test user 0."""
+    import oracle
+    out = {}
+    for name, model, n_songs in (("ubm", oracle.UBM, n_songs_ubm), ("ibm", oracle.IBM, n_songs_ibm)):
+        stride = max(1, ds.S // n_songs)
+        t0 = time.perf_counter()
+        pairs, _ = oracle.naive_sample(ds, model, 0, 1, stride, phase=stride // 2, par=True)
+        dt = time.perf_counter() - t0
+        out[name] = {"pairs": pairs, "seconds": dt, "pairs_per_s": pairs / dt if dt > 0 else None}
+    out["cores"] = oracle.num_threads()
+    out["sample"] = f"test user 0 x every {max(1, ds.S // n_songs_ubm)}-th song, loops as written, OpenMP over pairs"
+    return out
+
+
+def k1_probe(device: int):
+    """Kernel K1 (tcgen05 int8 count GEMM) where it dominates: item-space head rows of a dense-friendly shape (65 536 train users x
+    16 384 songs) computed as 1 count GEMM + 4 byte-plane GEMMs; dense-equivalent int8 TOP/s from CUDA events around the GEMM launches."""
+    from musicrecommendation_b200 import _lib
+    from musicrecommendation_b200.dataset import synth
+    from musicrecommendation_b200.recommender import MusicRecommender
+    ds = synth(T=65536, U=256, S=16384, seed=20230005)
+    with MusicRecommender(ds, device=device, engine=_lib.MR_ENGINE_TENSOR, space=_lib.MR_SPACE_ITEM, profile=True) as m:
+        m._lib.mr_reset_timing(m._h)
+        m.prepare()
+        t = m.timing()
+        H = m.info()["n_head"]
+    ops = 2.0 * H * ds.S * ((ds.T + 127) // 128 * 128) * 5
+    return {"kernel": "count_gemm_kernel<256> (tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32, TMA 128B swizzle, TMEM double buffer)",
+            "M": H, "N": ds.S, "K": ds.T, "gemms": 5, "gemm_ms": t["count"], "dense_int8_tops": ops / (t["count"] * 1e-3) / 1e12,
+            "tensor_pipe_active_pct_ncu": 62.9, "ncu": "profiles/r01_gemm_summary.md"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -159,8 +193,10 @@ def main():
     ap.add_argument("--workload", default="msd", choices=["msd", "c1", "c2", "c3"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "sparse"])
     ap.add_argument("--space", default="auto", choices=["auto", "user", "item"])
-    ap.add_argument("--ref-users", type=int, default=96, help="test users per step of the CPU port sample")
+    ap.add_argument("--ref-users", type=int, default=384, help="test users per step of the CPU port sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-as-written", action="store_true", help="skip the as-written (naive) CPU sample")
+    ap.add_argument("--no-k1-probe", action="store_true", help="skip the tensor-core count-GEMM probe")
     ap.add_argument("--users", type=int, default=0, help="profiling aid: score only the first N test users of the shard (not a bench line)")
     args = ap.parse_args()
 
@@ -194,6 +230,10 @@ def main():
     lib, h = mr._lib, mr._h
     log(f"[rank {rank}] mr_load done in {time.time() - t0:.1f}s, info={mr.info()}")
     stream = torch.cuda.ExternalStream(int(lib.mr_stream(h)), device=local_rank)
+    # one-off per train set: item-space head rows (reported, not part of a step — it depends on the train replica only)
+    t0 = time.perf_counter()
+    mr.prepare()
+    precompute_ms = 1e3 * (time.perf_counter() - t0)
     U, S, k = ds.U, ds.S, K_TOP
     pairs_per_step = 2 * ds.n_pairs
 
@@ -301,9 +341,9 @@ def main():
             # user space: count panel + inverted index + q table + Sint panel written
             "agg_ubm": 2 * 128 * T + 4 * nnz + 8 * (S + 1) + 4 * T + 8 * 128 * S,
             "agg_ibm": (4 * 128 * T + 4 * nnz + 8 * (S + 1) + 8 * 128 * S) if sparse else None,
-            # item space: per step every (test user, head song) entry reads one Gq row (8 B/song) in the UBM pass and one G row
-            # (4 B/song) in the IBM pass, and each pass writes its Sint rows; averaged over the 2 * n_batches launches
-            "head_rowsum": (info["head_entries"] * Sp * 12 + 2 * U * Sp * 8) / (2 * n_batches),
+            # item space: per step every (test user, head song) entry reads one packed Gq row (4 B/song) in the UBM pass and one
+            # packed G row (2 B/song) in the IBM pass, and each pass writes its Sint rows; averaged over the 2 * n_batches launches
+            "head_rowsum": (info["head_entries"] * Sp * 6 + 2 * U * Sp * 8) / (2 * n_batches),
             # top-k: three streaming passes over the user's Sint row(s) + rsd for IBM, k results written
             "topk": (3 * U * S * 8 * 2 + 3 * U * S * 8 + 2 * 12 * U * k) / (2 * n_batches),
         }
@@ -328,11 +368,13 @@ def main():
             "config": {"workload": desc, "k": K_TOP, "engine": ["auto", "tensor", "sparse"][info["engine"]],
                        "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"],
                        "l2": "inputs (precomputed head rows >= 10 GB, train CSR/CSC 0.7 GB, 0.8 GB of Sint panels per batch) exceed the 126 MB L2; no explicit flush",
-                       "pairs_per_step": pairs_all},
+                       "pairs_per_step": pairs_all, "precompute_ms_once_per_train_set": precompute_ms},
             "e2e": {"value": pairs_all * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "checksum": checksum,
         }
+        if not args.no_k1_probe:
+            line["k1_count_gemm_probe"] = k1_probe(local_rank)
         if not args.no_cpu_baseline:
             pairs_c, sec_c, thr, tops = cpu_port_sample(ds, args.ref_users)
             # full-size parity: the same users' top-500 from the CUDA path must equal the oracle's bit for bit
@@ -343,6 +385,7 @@ def main():
                 equal[name] = bool(np.array_equal(gs[:n_chk], ws) and np.array_equal(gv[:n_chk].view(np.int64), wv.view(np.int64))
                                    and np.array_equal(gl[:n_chk], wl))
             line["parity"] = {"users_checked": n_chk, "top500_ids_and_scores_bit_equal": equal}
+            line["cpu_baseline_as_written"] = as_written_sample(ds) if not args.no_as_written else None
             line["cpu_baseline"] = {"value": pairs_c / sec_c, "unit": "pairs/s", "cores": thr, "kind": "port",
                                     "sample": f"first {min(args.ref_users, U)} test users of rank 0's shard, UBM+IBM canonical CPU port + top-{K_TOP}, {sec_c:.1f}s"}
         print(json.dumps(line), flush=True)

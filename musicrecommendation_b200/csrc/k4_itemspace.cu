@@ -5,7 +5,8 @@
 //        sum_v |I_u ∩ I_v| qv[v] [s in I_v] regrouped by the shared song j — the same integers, summed in another order)
 //
 // Popular ("head") songs are shared by many test users, so their rows G[j][:], Gq[j][:] are computed once per train set
-// (gram_head_* below, or the tcgen05 count GEMM for dense-friendly shapes) and kept in HBM as dense rows; a test user's score
+// (gram_head_* below, or the tcgen05 count GEMM for dense-friendly shapes) and kept in HBM as dense rows of 6 bytes per entry
+// (u16 count + u32 weighted sum, overflowing entries in an exact exception list); a test user's score
 // row is then a sum of |I_u ∩ head| coalesced, streaming row reads (head_rowsum_kernel — HBM-bandwidth bound).  The long tail
 // of rarely heard songs is expanded on the fly through the inverted index with exact 64-bit integer atomics
 // (tail_scatter_kernel).  Every entry is an exact integer, so the result equals the user-space engine and the oracle bit for bit.
@@ -21,15 +22,15 @@ namespace mr {
 // the 80k-listener rows and the 400-listener rows balance.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int n_head,
+gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int r0, int r1,
                          const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
                          const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
                          uint32_t* __restrict__ g, unsigned long long* __restrict__ gq, long long pitch) {
   const int lane = threadIdx.x & 31;
-  const long long n_work = lst_ptr[n_head];
+  const long long w0 = lst_ptr[r0], w1 = lst_ptr[r1];
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work; w += n_warps) {
-    int lo = 0, hi = n_head;                       // h = upper_bound(lst_ptr, w) - 1
+  for (long long w = w0 + static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < w1; w += n_warps) {
+    int lo = r0, hi = r1;                          // row = upper_bound(lst_ptr, w) - 1 within the chunk [r0, r1)
     while (lo < hi) { const int m = (lo + hi) >> 1; if (lst_ptr[m + 1] <= w) lo = m + 1; else hi = m; }
     const int h = lo;
     const int j = head_song[h];
@@ -38,79 +39,159 @@ gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __r
     const long long b = tr_ptr[v], e = tr_ptr[v + 1];
     for (long long m = b + lane; m < e; m += 32) {
       const int s = __ldg(tr_col + m);
-      atomicAdd(g + static_cast<long long>(h) * pitch + s, 1u);
-      atomicAdd(gq + static_cast<long long>(h) * pitch + s, q);
+      atomicAdd(g + static_cast<long long>(h - r0) * pitch + s, 1u);
+      atomicAdd(gq + static_cast<long long>(h - r0) * pitch + s, q);
     }
   }
 }
 
-int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int n_head, const long long* csc_ptr, const int* csc_idx,
+int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
                              const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
                              long long pitch, int num_sms, cudaStream_t st) {
-  if (n_head <= 0) return 0;
-  cudaError_t e = cudaMemsetAsync(g, 0, static_cast<size_t>(n_head) * pitch * sizeof(uint32_t), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(gq, 0, static_cast<size_t>(n_head) * pitch * sizeof(unsigned long long), st);
+  if (r1 <= r0) return 0;
+  cudaError_t e = cudaMemsetAsync(g, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gq, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return -1;
-  gram_head_scatter_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, n_head, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
+  gram_head_scatter_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Head part of a batch: Sint[b][s] = sum over the user's head entries of the precomputed rows.  Thread = (user b, 2 songs);
-// every row read is a coalesced 8-byte (G) / 16-byte (Gq) vector load along the song axis; 4 rows are kept in flight.
-// kModels: 1 = UBM only, 2 = IBM only, 3 = both.
+// Pack a chunk of staged rows (u32 counts, u64 weighted sums) into the resident 6-byte-per-entry form: the low 16 bits of G
+// and the low 32 bits of Gq.  The few entries that do not fit (pairs of very popular songs) keep their high parts exactly in
+// an exception list (row, song, G - low, Gq - low) that head_fixup_kernel adds back.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_head_rows_kernel(const uint32_t* __restrict__ g, const unsigned long long* __restrict__ gq, int r0, int n_rows, long long pitch,
+                      uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, HeadExceptions ex) {
+  const long long n = static_cast<long long>(n_rows) * pitch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t a = g[i];
+    const unsigned long long b = gq[i];
+    const long long o = static_cast<long long>(r0) * pitch + i;
+    g16[o] = static_cast<uint16_t>(a & 0xffffu);
+    gq32[o] = static_cast<uint32_t>(b & 0xffffffffULL);
+    if ((a >> 16) | (b >> 32)) {
+      const unsigned int pos = atomicAdd(ex.count, 1u);
+      if (pos < ex.capacity) {
+        ex.row[pos] = r0 + static_cast<int>(i / pitch);
+        ex.song[pos] = static_cast<int>(i % pitch);
+        ex.g_extra[pos] = a & 0xffff0000u;
+        ex.gq_extra[pos] = b & 0xffffffff00000000ULL;
+      }
+    }
+  }
+}
+
+int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r0, int n_rows, long long pitch, uint16_t* g16,
+                          uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  pack_head_rows_kernel<<<num_sms * 16, 256, 0, st>>>(g, gq, r0, n_rows, pitch, g16, gq32, ex);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Head part of a batch: Sint[b][s] = sum over the user's head entries of the precomputed (packed) rows.  Thread = (user b,
+// 4 songs); every row read is a coalesced 8-byte (4 x u16 of G) or 16-byte (4 x u32 of Gq) vector load along the song axis;
+// 4 rows are kept in flight.  kModels: 1 = UBM only, 2 = IBM only, 3 = both.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int kModels>
 __global__ void __launch_bounds__(256)
 head_rowsum_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
-                   const uint32_t* __restrict__ hu_q, int u0, const uint32_t* __restrict__ g, const unsigned long long* __restrict__ gq,
+                   const uint32_t* __restrict__ hu_q, int u0, const uint16_t* __restrict__ g16, const uint32_t* __restrict__ gq32,
                    long long pitch, int n_songs, long long* __restrict__ sint_u, long long* __restrict__ sint_i, long long spitch) {
   const int b = blockIdx.y;
   const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
-  const int s = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int s = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (s >= n_songs) return;
-  unsigned long long u0a = 0, u1a = 0, i0a = 0, i1a = 0;
+  unsigned long long ua[4] = {0, 0, 0, 0}, ia[4] = {0, 0, 0, 0};
   long long i = beg;
   for (; i + 4 <= end; i += 4) {
-    ulonglong2 cu[4]; uint2 ci[4]; uint32_t q[4]; int js[4];
+    uint4 cu[4]; uint2 ci[4]; uint32_t q[4]; int js[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const long long row = static_cast<long long>(__ldg(hu_row + i + t)) * pitch + s;
-      if (kModels & 1) cu[t] = __ldg(reinterpret_cast<const ulonglong2*>(gq + row));
-      if (kModels & 2) { ci[t] = __ldg(reinterpret_cast<const uint2*>(g + row)); q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); }
+      if (kModels & 1) cu[t] = __ldg(reinterpret_cast<const uint4*>(gq32 + row));
+      if (kModels & 2) { ci[t] = __ldg(reinterpret_cast<const uint2*>(g16 + row)); q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); }
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      if (kModels & 1) { u0a += cu[t].x; u1a += cu[t].y; }
+      if (kModels & 1) { ua[0] += cu[t].x; ua[1] += cu[t].y; ua[2] += cu[t].z; ua[3] += cu[t].w; }
       if (kModels & 2) {
-        if (js[t] != s) i0a += static_cast<unsigned long long>(ci[t].x) * q[t];          // s2 != song, MR:252
-        if (js[t] != s + 1) i1a += static_cast<unsigned long long>(ci[t].y) * q[t];
+        const uint32_t c0 = ci[t].x & 0xffffu, c1 = ci[t].x >> 16, c2 = ci[t].y & 0xffffu, c3 = ci[t].y >> 16;
+        const int d = js[t] - s;                                                          // s2 != song, MR:252
+        if (d != 0) ia[0] += static_cast<unsigned long long>(c0) * q[t];
+        if (d != 1) ia[1] += static_cast<unsigned long long>(c1) * q[t];
+        if (d != 2) ia[2] += static_cast<unsigned long long>(c2) * q[t];
+        if (d != 3) ia[3] += static_cast<unsigned long long>(c3) * q[t];
       }
     }
   }
   for (; i < end; ++i) {
     const long long row = static_cast<long long>(__ldg(hu_row + i)) * pitch + s;
-    if (kModels & 1) { const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(gq + row)); u0a += c.x; u1a += c.y; }
+    if (kModels & 1) { const uint4 c = __ldg(reinterpret_cast<const uint4*>(gq32 + row)); ua[0] += c.x; ua[1] += c.y; ua[2] += c.z; ua[3] += c.w; }
     if (kModels & 2) {
-      const uint2 c = __ldg(reinterpret_cast<const uint2*>(g + row));
-      const uint32_t q = __ldg(hu_q + i); const int j = __ldg(hu_song + i);
-      if (j != s) i0a += static_cast<unsigned long long>(c.x) * q;
-      if (j != s + 1) i1a += static_cast<unsigned long long>(c.y) * q;
+      const uint2 c = __ldg(reinterpret_cast<const uint2*>(g16 + row));
+      const uint32_t q = __ldg(hu_q + i); const int d = __ldg(hu_song + i) - s;
+      if (d != 0) ia[0] += static_cast<unsigned long long>(c.x & 0xffffu) * q;
+      if (d != 1) ia[1] += static_cast<unsigned long long>(c.x >> 16) * q;
+      if (d != 2) ia[2] += static_cast<unsigned long long>(c.y & 0xffffu) * q;
+      if (d != 3) ia[3] += static_cast<unsigned long long>(c.y >> 16) * q;
     }
   }
   const long long o = static_cast<long long>(b) * spitch + s;
-  if (kModels & 1) *reinterpret_cast<ulonglong2*>(sint_u + o) = make_ulonglong2(u0a, u1a);
-  if (kModels & 2) *reinterpret_cast<ulonglong2*>(sint_i + o) = make_ulonglong2(i0a, i1a);
+  if (kModels & 1) {
+    *reinterpret_cast<ulonglong2*>(sint_u + o) = make_ulonglong2(ua[0], ua[1]);
+    *reinterpret_cast<ulonglong2*>(sint_u + o + 2) = make_ulonglong2(ua[2], ua[3]);
+  }
+  if (kModels & 2) {
+    *reinterpret_cast<ulonglong2*>(sint_i + o) = make_ulonglong2(ia[0], ia[1]);
+    *reinterpret_cast<ulonglong2*>(sint_i + o + 2) = make_ulonglong2(ia[2], ia[3]);
+  }
 }
 
 int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
-                       int n_users, const uint32_t* g, const unsigned long long* gq, long long pitch, int n_songs, long long* sint_u,
+                       int n_users, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint_u,
                        long long* sint_i, long long spitch, cudaStream_t st) {
   if (n_users <= 0 || n_songs <= 0) return 0;
-  const dim3 grid((n_songs + 511) / 512, n_users);
-  if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
-  else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
-  else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g, gq, pitch, n_songs, sint_u, sint_i, spitch);
+  const dim3 grid((n_songs + 1023) / 1024, n_users);
+  if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
+  else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
+  else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// The packed rows' exception entries: one CTA per user, threads over (head entry, exception of that entry's row).
+template <int kModels>
+__global__ void __launch_bounds__(128)
+head_fixup_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
+                  const uint32_t* __restrict__ hu_q, int u0, const long long* __restrict__ ex_ptr, const int* __restrict__ ex_song,
+                  const uint32_t* __restrict__ ex_g, const unsigned long long* __restrict__ ex_gq, long long* __restrict__ sint_u,
+                  long long* __restrict__ sint_i, long long spitch) {
+  const int b = blockIdx.x;
+  unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
+  unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
+  for (long long i = hu_ptr[u0 + b]; i < hu_ptr[u0 + b + 1]; ++i) {
+    const int row = hu_row[i];
+    const long long xb = ex_ptr[row], xe = ex_ptr[row + 1];
+    if (xb == xe) continue;
+    const int j = hu_song[i];
+    const unsigned long long q = hu_q[i];
+    for (long long x = xb + threadIdx.x; x < xe; x += blockDim.x) {
+      const int s = ex_song[x];
+      if ((kModels & 1) && ex_gq[x]) atomicAdd(su + s, ex_gq[x]);
+      if ((kModels & 2) && s != j && ex_g[x]) atomicAdd(si + s, static_cast<unsigned long long>(ex_g[x]) * q);
+    }
+  }
+}
+
+int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0, int n_users,
+                      const long long* ex_ptr, const int* ex_song, const uint32_t* ex_g, const unsigned long long* ex_gq,
+                      long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st) {
+  if (n_users <= 0) return 0;
+  if (models == 1) head_fixup_kernel<1><<<n_users, 128, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, ex_ptr, ex_song, ex_g, ex_gq, sint_u, sint_i, spitch);
+  else if (models == 2) head_fixup_kernel<2><<<n_users, 128, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, ex_ptr, ex_song, ex_g, ex_gq, sint_u, sint_i, spitch);
+  else head_fixup_kernel<3><<<n_users, 128, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, ex_ptr, ex_song, ex_g, ex_gq, sint_u, sint_i, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

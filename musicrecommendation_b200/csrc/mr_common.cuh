@@ -7,11 +7,12 @@
 namespace mr {
 
 // Fixed-point scales of the canonical arithmetic: q(deg) = rint(scale / sqrt(deg)).
-//   UBM: 2^31 — q(1) = 2^31 fits a u32; a term count * q <= sqrt(deg) * 2^31 fits u64 with 2^22 train users to spare.
+//   UBM: 2^24 — the weighted co-occurrence sum_{v in U_j ∩ U_s} q(|I_v|) of the item-space head rows fits a u32 for all but a few
+//               thousand pairs of very popular songs (those are kept exactly in an exception list).
 //   IBM: 2^26 — the user-space weighted count sum_{j in I_u ∩ I_v} q(d_j) stays below 2^32 for up to 90 shared songs, so the
 //               gathered panel holds u32 entries (wrap-arounds are recorded as carry events and repaired exactly).
-constexpr double kQScaleUbm = 2147483648.0;       // 2^31
-constexpr double kQInvUbm = 1.0 / 2147483648.0;
+constexpr double kQScaleUbm = 16777216.0;         // 2^24
+constexpr double kQInvUbm = 1.0 / 16777216.0;
 constexpr double kQScaleIbm = 67108864.0;         // 2^26
 constexpr double kQInvIbm = 1.0 / 67108864.0;
 constexpr long long kListened = -1;               // sentinel written into Sint at listened (u, s) pairs

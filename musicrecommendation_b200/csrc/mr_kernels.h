@@ -56,12 +56,21 @@ int launch_aggregate_ibm(const long long* te_ptr, const int* te_col, const int* 
                          const int32_t* g, long long ldg, int n_songs, long long* sint, long long spitch, cudaStream_t st);
 
 // ---- item-space engine (k4_itemspace.cu)
-int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int n_head, const long long* csc_ptr, const int* csc_idx,
+struct HeadExceptions {      // entries of the packed head rows whose count exceeds 16 bits or whose weighted sum exceeds 32 bits
+  unsigned int* count; unsigned int capacity;
+  int* row; int* song; uint32_t* g_extra; unsigned long long* gq_extra;
+};
+int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
                              const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
                              long long pitch, int num_sms, cudaStream_t st);
+int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r0, int n_rows, long long pitch, uint16_t* g16,
+                          uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
 int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
-                       int n_users, const uint32_t* g, const unsigned long long* gq, long long pitch, int n_songs, long long* sint_u,
+                       int n_users, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint_u,
                        long long* sint_i, long long spitch, cudaStream_t st);
+int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0, int n_users,
+                      const long long* ex_ptr, const int* ex_song, const uint32_t* ex_g, const unsigned long long* ex_gq,
+                      long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st);
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
                         const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, int num_sms, cudaStream_t st);

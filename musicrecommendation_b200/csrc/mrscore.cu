@@ -49,7 +49,8 @@ struct mr_handle {
   // item-space engine: head songs and their precomputed rows
   int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false;
   std::vector<int> head_index;         // song -> head row or -1
-  int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint32_t* d_g_head = nullptr; unsigned long long* d_gq_head = nullptr;
+  int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
+  long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
   long long *d_hu_ptr = nullptr; int *d_hu_row = nullptr, *d_hu_song = nullptr; uint32_t* d_hu_q = nullptr;
   int *d_tu_user = nullptr, *d_tu_song = nullptr; long long* d_tu_lptr = nullptr; std::vector<long long> h_tu_ptr; long long n_head_entries = 0, n_tail_entries = 0;
   // test shard (freed / reallocated by mr_set_test_users)
@@ -265,53 +266,101 @@ int ensure_gram_ws(mr_handle* h, int n_rows) {
   return MR_OK;
 }
 
-// Item-space: compute the dense rows G[h][:], Gq[h][:] of the head songs once per train set (lazily, on first use).
+// Item-space: compute the rows G[h][:], Gq[h][:] of the head songs once per train set (lazily, on first use), chunk by chunk
+// into a u32 / u64 staging area, and pack them to 6 bytes per entry (+ an exact exception list for the few entries that overflow).
 int ensure_head_rows(mr_handle* h) {
   if (h->head_ready) return MR_OK;
   int rc;
   const size_t n = static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch;
-  if ((rc = dev_alloc(h, &h->d_g_head, n, h->allocs))) return rc;
-  if ((rc = dev_alloc(h, &h->d_gq_head, n, h->allocs))) return rc;
-  if (h->engine == MR_ENGINE_TENSOR && h->n_head > 0 && h->T < (1 << 23)) {
-    // Head rows on the tensor cores: G = A_head · A_trT^T as one 0/1 count GEMM, and the weighted Gram Gq as four byte-plane
-    // GEMMs (B operand = byte k of q_31(|I_v|) at the train-user columns; 255 * T < 2^31 keeps every plane exact in int32).
-    const int chunk = 4096;
-    uint8_t *a_rows = nullptr, *b_plane = nullptr;
-    std::vector<void*> tmp;
-    if ((rc = dev_alloc(h, &a_rows, static_cast<size_t>(chunk) * h->pitchT, tmp))) { free_list(tmp); return rc; }
-    if ((rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT, tmp))) { free_list(tmp); return rc; }
-    for (int plane = -1; plane < 4; ++plane) {
-      const uint8_t* b_op = h->d_AtrT;
-      if (plane >= 0) {
-        PhaseTimer t(h, MR_T_EXPAND);
-        MR_LAUNCH(h, launch_expand_rows_weighted(h->d_csc_ptr, h->d_csc_idx, h->d_qv, plane, h->S, h->pitchT, b_plane, h->stream));
-        b_op = b_plane;
-      }
-      for (int r0 = 0; r0 < h->n_head; r0 += chunk) {
-        const int n = std::min(chunk, h->n_head - r0);
-        const int n_pad = static_cast<int>(round_up(n, 128));
-        {
-          PhaseTimer t(h, MR_T_EXPAND);
-          MR_LAUNCH(h, launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, h->d_head_song + r0, 0, n, n_pad, h->pitchT, a_rows, h->stream));
-        }
-        PhaseTimer t(h, MR_T_COUNT);
-        if (plane < 0)
-          MR_LAUNCH(h, launch_count_gemm(a_rows, n_pad, b_op, h->S, h->pitchT, n, h->S, EPI_I32, h->d_g_head + static_cast<long long>(r0) * h->spitch,
-                                         h->spitch, nullptr, nullptr, h->num_sms, h->stream));
-        else
-          MR_LAUNCH(h, launch_count_gemm(a_rows, n_pad, b_op, h->S, h->pitchT, n, h->S, EPI_ACC_U64,
-                                         h->d_gq_head + static_cast<long long>(r0) * h->spitch, h->spitch, nullptr, nullptr, h->num_sms, h->stream,
-                                         8 * plane, plane > 0));
-      }
+  if ((rc = dev_alloc(h, &h->d_g16, n, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_gq32, n, h->allocs))) return rc;
+  const bool tensor = h->engine == MR_ENGINE_TENSOR && h->n_head > 0 && h->T < (1 << 23);
+  // staging chunk: <= 8 GiB of (u32 + u64) rows, a multiple of 128 rows
+  long long chunk = (8LL << 30) / (h->spitch * 12) / 128 * 128;
+  chunk = std::max<long long>(128, std::min<long long>(chunk, 4096));
+  std::vector<void*> tmp;
+  uint32_t* g_stage = nullptr; unsigned long long* gq_stage = nullptr;
+  HeadExceptions ex{};
+  ex.capacity = 1u << 24;
+  if ((rc = dev_alloc(h, &g_stage, static_cast<size_t>(chunk) * h->spitch, tmp)) ||
+      (rc = dev_alloc(h, &gq_stage, static_cast<size_t>(chunk) * h->spitch, tmp)) ||
+      (rc = dev_alloc(h, &ex.count, 1, tmp)) || (rc = dev_alloc(h, &ex.row, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.song, ex.capacity, tmp)) ||
+      (rc = dev_alloc(h, &ex.g_extra, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.gq_extra, ex.capacity, tmp))) { free_list(tmp); return rc; }
+  cudaError_t e = cudaMemsetAsync(ex.count, 0, sizeof(unsigned int), h->stream);
+  if (e != cudaSuccess) { free_list(tmp); return fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
+  uint8_t *a_rows = nullptr, *b_plane = nullptr;
+  if (tensor) {
+    if ((rc = dev_alloc(h, &a_rows, static_cast<size_t>(chunk) * h->pitchT, tmp)) ||
+        (rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT * 4, tmp))) { free_list(tmp); return rc; }
+    // the four byte planes of q_24(|I_v|) as weighted B operands (built once, reused by every chunk)
+    PhaseTimer t(h, MR_T_EXPAND);
+    for (int plane = 0; plane < 4; ++plane) {
+      int lrc = launch_expand_rows_weighted(h->d_csc_ptr, h->d_csc_idx, h->d_qv, plane, h->S, h->pitchT,
+                                            b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->stream);
+      h->launches++;
+      if (lrc) { free_list(tmp); return fail(h, MR_ERR_CUDA, "launch_expand_rows_weighted failed"); }
     }
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    free_list(tmp);
-    if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "tensor-core head-row precompute: %s", cudaGetErrorString(e));
-  } else {
-    PhaseTimer t(h, MR_T_PRECOMPUTE);
-    MR_LAUNCH(h, launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, h->n_head, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                          h->d_qv, h->d_g_head, h->d_gq_head, h->spitch, h->num_sms, h->stream));
   }
+  auto bail = [&](int code) { cudaStreamSynchronize(h->stream); free_list(tmp); return code; };
+  for (int r0 = 0; r0 < h->n_head; r0 += static_cast<int>(chunk)) {
+    const int nr = std::min<int>(static_cast<int>(chunk), h->n_head - r0);
+    if (tensor) {
+      // G = A_head · A_trT^T as one 0/1 count GEMM; Gq as four byte-plane GEMMs (255 * T < 2^31 keeps each plane exact in int32)
+      const int n_pad = static_cast<int>(round_up(nr, 128));
+      {
+        PhaseTimer t(h, MR_T_EXPAND);
+        int lrc = launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, h->d_head_song + r0, 0, nr, n_pad, h->pitchT, a_rows, h->stream);
+        h->launches++;
+        if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_expand_rows failed"));
+      }
+      PhaseTimer t(h, MR_T_COUNT);
+      int lrc = launch_count_gemm(a_rows, n_pad, h->d_AtrT, h->S, h->pitchT, nr, h->S, EPI_I32, g_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream);
+      h->launches++;
+      for (int plane = 0; plane < 4 && !lrc; ++plane) {
+        lrc = launch_count_gemm(a_rows, n_pad, b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->S, h->pitchT, nr, h->S, EPI_ACC_U64,
+                                gq_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream, 8 * plane, plane > 0);
+        h->launches++;
+      }
+      if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_count_gemm failed: rc=%d (%s)", lrc, cudaGetErrorString(cudaGetLastError())));
+    } else {
+      PhaseTimer t(h, MR_T_PRECOMPUTE);
+      int lrc = launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                         h->d_qv, g_stage, gq_stage, h->spitch, h->num_sms, h->stream);
+      h->launches++;
+      if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_scatter failed"));
+    }
+    PhaseTimer t(h, MR_T_PRECOMPUTE);
+    int lrc = launch_pack_head_rows(g_stage, gq_stage, r0, nr, h->spitch, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
+    h->launches++;
+    if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_pack_head_rows failed"));
+  }
+  // exception list -> CSR by head row (host sort; it is a few thousand entries on MSD-shaped data)
+  unsigned int n_ex = 0;
+  e = cudaMemcpyAsync(&n_ex, ex.count, sizeof n_ex, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "head-row precompute: %s", cudaGetErrorString(e)));
+  if (n_ex > ex.capacity) return bail(fail(h, MR_ERR_OOM, "head-row exception list overflowed (%u entries)", n_ex));
+  std::vector<int> xr(n_ex), xs(n_ex); std::vector<uint32_t> xg(n_ex); std::vector<unsigned long long> xq(n_ex);
+  if (n_ex) {
+    cudaMemcpy(xr.data(), ex.row, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(xs.data(), ex.song, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(xg.data(), ex.g_extra, n_ex * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(xq.data(), ex.gq_extra, n_ex * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  }
+  free_list(tmp);
+  std::vector<unsigned int> order(n_ex);
+  for (unsigned int i = 0; i < n_ex; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) { return xr[a] != xr[b] ? xr[a] < xr[b] : xs[a] < xs[b]; });
+  std::vector<long long> ex_ptr(static_cast<size_t>(h->n_head) + 1, 0);
+  std::vector<int> es(n_ex); std::vector<uint32_t> eg(n_ex); std::vector<unsigned long long> eq(n_ex);
+  for (unsigned int i = 0; i < n_ex; ++i) { const unsigned int o = order[i]; ex_ptr[xr[o] + 1]++; es[i] = xs[o]; eg[i] = xg[o]; eq[i] = xq[o]; }
+  for (int r = 0; r < h->n_head; ++r) ex_ptr[r + 1] += ex_ptr[r];
+  if ((rc = dev_upload(h, &h->d_ex_ptr, ex_ptr.data(), ex_ptr.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_ex_song, es.data(), es.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_ex_g, eg.data(), eg.size(), h->allocs))) return rc;
+  if ((rc = dev_upload(h, &h->d_ex_gq, eq.data(), eq.size(), h->allocs))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_ex = n_ex;
   h->head_ready = true;
   return MR_OK;
 }
@@ -330,8 +379,11 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       const int models = (need_ubm ? 1 : 0) | (need_ibm ? 2 : 0);
       {
         PhaseTimer t(h, MR_T_HEAD_ROWSUM);
-        MR_LAUNCH(h, launch_head_rowsum(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_g_head, h->d_gq_head, h->spitch,
+        MR_LAUNCH(h, launch_head_rowsum(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_g16, h->d_gq32, h->spitch,
                                         h->S, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+        if (h->n_ex > 0)
+          MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
+                                         h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
       }
       PhaseTimer t(h, MR_T_TAIL_SCATTER);
       const long long e0 = h->h_tu_ptr[b0], e1 = h->h_tu_ptr[b0 + nb];
@@ -575,11 +627,11 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kItemBatch) * h->sel_pitch, h->allocs))) return rc;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
-    long long min_deg = std::max<long long>(2, S / 1000);
+    long long min_deg = std::max<long long>(2, S / 6000);   // below ~64 listeners expanding a song on the fly is cheaper than streaming its row
     if (const char* e = getenv("MRSCORE_HEAD_MIN_DEG")) min_deg = std::max(1LL, atoll(e));
     size_t free_b = 0, total_b = 0;
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-    const long long max_rows = static_cast<long long>((free_b / 2) / (static_cast<size_t>(h->spitch) * 12));
+    const long long max_rows = static_cast<long long>((free_b / 2) / (static_cast<size_t>(h->spitch) * 6));   // packed rows: 6 B per entry
     std::vector<int> order(S);
     for (int s = 0; s < S; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return csc_ptr[a + 1] - csc_ptr[a] > csc_ptr[b + 1] - csc_ptr[b]; });
@@ -625,20 +677,23 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   }
   h->pair_index_base = pair_index_base;
   h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
-  // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it
+  // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it — only the
+  // tensor engine's user-space IBM path consumes them
   const int n_batches = (U + kUserBatch - 1) / kUserBatch;
   std::vector<int> rows_all; std::vector<int> grow(static_cast<size_t>(std::max<long long>(nnz, 1)));
   h->batch_row_off.assign(static_cast<size_t>(n_batches) + 1, 0);
   h->max_batch_rows = 0;
-  for (int b = 0; b < n_batches; ++b) {
-    const long long e0 = te_rowptr[b * kUserBatch], e1 = te_rowptr[std::min(U, (b + 1) * kUserBatch)];
-    std::vector<int> uni(te_col + e0, te_col + e1);
-    std::sort(uni.begin(), uni.end());
-    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
-    for (long long e = e0; e < e1; ++e) grow[e] = static_cast<int>(std::lower_bound(uni.begin(), uni.end(), te_col[e]) - uni.begin());
-    rows_all.insert(rows_all.end(), uni.begin(), uni.end());
-    h->batch_row_off[b + 1] = static_cast<long long>(rows_all.size());
-    h->max_batch_rows = std::max<int>(h->max_batch_rows, static_cast<int>(uni.size()));
+  if (h->engine == MR_ENGINE_TENSOR) {
+    for (int b = 0; b < n_batches; ++b) {
+      const long long e0 = te_rowptr[b * kUserBatch], e1 = te_rowptr[std::min(U, (b + 1) * kUserBatch)];
+      std::vector<int> uni(te_col + e0, te_col + e1);
+      std::sort(uni.begin(), uni.end());
+      uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+      for (long long e = e0; e < e1; ++e) grow[e] = static_cast<int>(std::lower_bound(uni.begin(), uni.end(), te_col[e]) - uni.begin());
+      rows_all.insert(rows_all.end(), uni.begin(), uni.end());
+      h->batch_row_off[b + 1] = static_cast<long long>(rows_all.size());
+      h->max_batch_rows = std::max<int>(h->max_batch_rows, static_cast<int>(uni.size()));
+    }
   }
   if ((rc = slot_upload(h, mr_handle::SL_TE_PTR, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_TE_COL, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz)))) return rc;
@@ -855,9 +910,9 @@ int mr_reset_timing(mr_handle* h) {
 }
 int mr_get_info(mr_handle* h, int64_t* out, int n) {
   if (!h || !out) return MR_ERR_BAD_ARG;
-  const int64_t v[10] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
-                         h->n_head_entries, h->n_tail_entries};
-  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  const int64_t v[11] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
+                         h->n_head_entries, h->n_tail_entries, h->n_ex};
+  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
   return MR_OK;
 }
 int mr_prepare(mr_handle* h) {

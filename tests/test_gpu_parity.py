@@ -128,7 +128,10 @@ def test_popular_songs_split_across_warps(engine, oracle_lib):
     """Songs with more than 4096 train listeners are aggregated by several warps with 64-bit integer atomics: still exact."""
     ds = synth(T=12000, U=200, S=30000, seed=6)
     assert np.bincount(ds.tr_col).max() > 4096
-    check_dataset(ds, oracle_lib, engine, blends=False)
+    info = check_dataset(ds, oracle_lib, engine, blends=False)
+    if engine["space"] == _lib.MR_SPACE_ITEM:
+        # pairs of very popular songs overflow the packed 16 / 32-bit head-row entries and live in the exact exception list
+        assert info["head_exceptions"] > 0
 
 
 def test_long_rows_take_the_sampled_topk_path(oracle_lib):
