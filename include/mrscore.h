@@ -94,6 +94,11 @@ int mr_prepare(mr_handle* h);
 int mr_counts_ubm(mr_handle* h, int32_t* out_UxT);
 int mr_counts_ibm(mr_handle* h, int s0, int s1, int32_t* out_rows);
 
+/* Device-resident variant for the K-split item-item sweep (BASELINE configs[4], DIST:459-461 song partitioning): rows [s0,s1) of
+ * this handle's PARTIAL co-occurrence matrix (its train-user shard only) stay in HBM as int32 [s1-s0][*ld]; the caller sums the
+ * partial panels of all ranks with one NCCL reduce-scatter.  The pointer is valid until the next call on the handle. */
+int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t* ld);
+
 /* Cosine similarities with the normalisation fused into the GEMM epilogue (fp32): user-user MR:140-149 and rows [s0,s1) of
  * item-item MR:230-239 (denominator uses the train+test listener counts, MR:237). */
 int mr_similarity_ubm(mr_handle* h, float* out_UxT);

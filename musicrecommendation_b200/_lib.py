@@ -15,7 +15,7 @@ MR_SPACE_AUTO, MR_SPACE_USER, MR_SPACE_ITEM = 0, 8, 16
 TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
 
 # every symbol include/mrscore.h declares
-SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm",
+SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_topk", "mr_topk_device",
            "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
 
@@ -49,6 +49,7 @@ def load():
     lib.mr_prepare.argtypes = [vp]
     lib.mr_counts_ubm.argtypes = [vp, vp]
     lib.mr_counts_ibm.argtypes = [vp, i32, i32, vp]
+    lib.mr_gram_rows_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
     lib.mr_similarity_ubm.argtypes = [vp, vp]
     lib.mr_similarity_ibm.argtypes = [vp, i32, i32, vp]
     lib.mr_score_dense.argtypes = [vp, i32, vp]

@@ -100,9 +100,11 @@ __global__ void __launch_bounds__(256)
 head_rowsum_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
                    const uint32_t* __restrict__ hu_q, int u0, const uint16_t* __restrict__ g16, const uint32_t* __restrict__ gq32,
                    long long pitch, int n_songs, long long* __restrict__ sint_u, long long* __restrict__ sint_i, long long spitch) {
-  const int b = blockIdx.y;
+  // blockIdx.x = user, blockIdx.y = song tile: CTAs that are resident together work on the SAME song tile for different users, so
+  // the row tiles of popular songs (shared by many users of the batch) are fetched from HBM once and hit in L2 for the others
+  const int b = blockIdx.x;
   const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
-  const int s = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int s = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
   if (s >= n_songs) return;
   unsigned long long ua[4] = {0, 0, 0, 0}, ia[4] = {0, 0, 0, 0};
   long long i = beg;
@@ -154,7 +156,7 @@ int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, c
                        int n_users, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint_u,
                        long long* sint_i, long long spitch, cudaStream_t st) {
   if (n_users <= 0 || n_songs <= 0) return 0;
-  const dim3 grid((n_songs + 1023) / 1024, n_users);
+  const dim3 grid(n_users, (n_songs + 1023) / 1024);
   if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
   else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
   else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);

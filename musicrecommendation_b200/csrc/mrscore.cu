@@ -57,7 +57,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -801,6 +801,24 @@ static int gram_range(mr_handle* h, int s0, int s1, int32_t* out_i32, float* out
     if (e != cudaSuccess) { free_list(tmp); return fail(h, MR_ERR_CUDA, "gram rows copy-out: %s", cudaGetErrorString(e)); }
   }
   free_list(tmp);
+  return MR_OK;
+}
+
+int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t* ld) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  if (!dev_out || !ld) return fail(h, MR_ERR_BAD_ARG, "null output");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  if (s0 < 0 || s1 > h->S || s0 >= s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
+  const int n = s1 - s0;
+  int rc = ensure_gram_ws(h, n);
+  if (rc) return rc;
+  int* d_ids = nullptr;
+  if ((rc = slot_alloc(h, mr_handle::SL_GRAM_IDS, &d_ids, static_cast<size_t>(n)))) return rc;
+  iota_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_ids, s0, n);
+  h->launches++;
+  if ((rc = gram_rows(h, d_ids, n))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  *dev_out = h->d_g; *ld = h->ldg;
   return MR_OK;
 }
 

@@ -57,3 +57,31 @@ def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, 
         dist.all_gather(buf, p, group=group)
         outs.append(torch.cat([b[: hi - lo] for b, (lo, hi) in zip(buf, sizes)]))
     return tuple(outs)
+
+
+def split_train_users(ds: Dataset, rank: int, world: int) -> Dataset:
+    """K-split of the item-item Gram (BASELINE configs[4]): rank r keeps the train users of its contiguous range, every song.
+    deg_song stays global — the cosine denominators count all listeners (MR:237)."""
+    v0, v1 = shard_range(ds.T, rank, world)
+    a, b = int(ds.tr_ptr[v0]), int(ds.tr_ptr[v1])
+    return Dataset(v1 - v0, ds.U, ds.S, (ds.tr_ptr[v0:v1 + 1] - a).astype(np.int64), ds.tr_col[a:b], ds.te_ptr, ds.te_col, ds.lab_ptr,
+                   ds.lab_col, ds.deg_tr[v0:v1], ds.deg_te, ds.deg_song, None, ds.test_users, ds.songs, dict(ds.meta, train_shard=(v0, v1)))
+
+
+def reduce_scatter_rows(partial, world: int, rank: int, group=None):
+    """Sum the ranks' partial int32 panels [n, ld] and leave rows [rank*n/world, (rank+1)*n/world) on each rank: one NCCL
+    reduce-scatter (integer sums: bit-exact in any reduction order).  n must be a multiple of world.  gloo (CPU tests) has no
+    reduce-scatter, so it all-reduces and slices."""
+    import torch
+    import torch.distributed as dist
+    n = partial.shape[0]
+    assert n % world == 0
+    if world == 1:
+        return partial
+    if dist.get_backend(group) == "gloo":
+        full = partial.clone()
+        dist.all_reduce(full, group=group)
+        return full[rank * (n // world):(rank + 1) * (n // world)]
+    out = torch.empty((n // world, partial.shape[1]), dtype=partial.dtype, device=partial.device)
+    dist.reduce_scatter_tensor(out, partial.contiguous(), group=group)
+    return out

@@ -267,6 +267,16 @@ class MusicRecommender:
         self._check(self._lib.mr_counts_ibm(self._h, s0, s1, _p(out)))
         return out
 
+    def gram_rows_device(self, s0: int, s1: int):
+        """Rows [s0,s1) of this handle's (partial) train co-occurrence matrix as a torch int32 view [s1-s0, ld] of device memory."""
+        import torch
+        ptr, ld = C.c_void_p(), C.c_int64()
+        self._check(self._lib.mr_gram_rows_device(self._h, s0, s1, C.byref(ptr), C.byref(ld)))
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (s1 - s0, ld.value), "typestr": "<i4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
     def similarity_ubm(self) -> np.ndarray:
         out = np.empty((self.ds.U, self.ds.T), np.float32)
         self._check(self._lib.mr_similarity_ubm(self._h, _p(out)))

@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from musicrecommendation_b200.dataset import synth
-from musicrecommendation_b200.distributed import shard_range, pair_index_bases, gather_topk
+from musicrecommendation_b200.distributed import shard_range, pair_index_bases, gather_topk, split_train_users, reduce_scatter_rows
 
 
 def _free_port():
@@ -46,6 +46,10 @@ def _worker(rank, world, port, out_dir):
         song, score, ln = oracle.topk(model, 50)
         g = gather_topk(song, score, ln, ds.U, world, rank)
         results[name] = [t.numpy() for t in g]
+    # K-split of the item-item Gram: partial panels of the ranks' train-user shards, summed and row-scattered
+    part = torch.from_numpy(oracle.gram_rows(split_train_users(ds, rank, world), np.arange(0, 64)))
+    mine = reduce_scatter_rows(part, world, rank)
+    np.save(os.path.join(out_dir, f"gram_rows_rank{rank}.npy"), mine.numpy())
     if rank == 0:
         np.savez(os.path.join(out_dir, "gathered.npz"), **{f"{k}_{i}": v for k, vs in results.items() for i, v in enumerate(vs)})
     dist.barrier()
@@ -68,6 +72,9 @@ def test_two_process_gloo_gather_matches_single_process(tmp_path, oracle_lib):
     ubm = oracle_lib.canon_scores(ds, oracle_lib.UBM)
     ibm = oracle_lib.canon_scores(ds, oracle_lib.IBM)
     want = {"ubm": ubm, "agg": oracle_lib.blend_dense(oracle_lib.AGG, 0.5, ubm, ibm), "stoch": oracle_lib.blend_dense(oracle_lib.STOCH, 0.5, ubm, ibm, seed=5)}
+    full = oracle_lib.gram_rows(ds, np.arange(0, 64))
+    for r in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / f"gram_rows_rank{r}.npy"), full[r * 32:(r + 1) * 32])
     for name, model in want.items():
         ws, wv, wl = oracle_lib.topk(model, 50)
         np.testing.assert_array_equal(got[f"{name}_0"], ws)
