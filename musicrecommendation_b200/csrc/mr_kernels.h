@@ -6,7 +6,9 @@
 namespace mr {
 
 constexpr int kUserBatch = 128;   // test users per batch of the user-space engine = UMMA M
-constexpr int kItemBatch = 296;   // test users per batch of the item-space engine = 2 top-k CTAs per SM on 148 SMs
+constexpr int kItemBatch = 1184;  // test users per batch of the item-space engine = 8 waves of top-k CTAs on 148 SMs; a large batch lets
+                                  // users that share a popular song reuse its row tile out of L2 (head_rowsum_kernel)
+constexpr int kTailSubBatch = 296; // tail scatter runs per 296 users so its atomics stay within a ~1.8 GB slice of the Sint panels
 // Count panels K1 hands to K2, train-user-major so that one gathered row serves the whole 128-user batch in one coalesced read:
 //   UBM  u16 Ct[T][128]   256-byte rows     IBM (user space)  u32 Wi[T][128]   512-byte rows
 // (A sub-panel-major variant with 32-byte, L2-resident rows was measured 1.7-1.9x slower on B200: random 32-byte sector

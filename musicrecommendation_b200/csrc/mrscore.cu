@@ -47,7 +47,7 @@ struct mr_handle {
   long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
   uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
   // item-space engine: head songs and their precomputed rows
-  int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false;
+  int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false; int item_batch = kItemBatch;
   std::vector<int> head_index;         // song -> head row or -1
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
   long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
@@ -372,7 +372,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
   const bool need_ibm = model != MODEL_UBM && mode != RUN_COUNTS_UBM && mode != RUN_SIM_UBM;
   const bool item_space = h->space == MR_SPACE_ITEM && (mode == RUN_TOPK || mode == RUN_DENSE);
   if (item_space) { int rc = ensure_head_rows(h); if (rc) return rc; }
-  const int batch = item_space ? kItemBatch : kUserBatch;
+  const int batch = item_space ? h->item_batch : kUserBatch;
   for (int b0 = 0; b0 < h->U; b0 += batch) {
     const int nb = std::min(batch, h->U - b0);
     if (item_space) {
@@ -386,9 +386,12 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
                                          h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
       }
       PhaseTimer t(h, MR_T_TAIL_SCATTER);
-      const long long e0 = h->h_tu_ptr[b0], e1 = h->h_tu_ptr[b0 + nb];
-      MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                       h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->num_sms, h->stream));
+      for (int s0 = 0; s0 < nb; s0 += kTailSubBatch) {
+        const int sn = std::min(kTailSubBatch, nb - s0);
+        const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
+        MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
+                                         h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->num_sms, h->stream));
+      }
     } else if (need_ubm) {
       int rc = count_ubm_batch(h, b0, nb);
       if (rc) return rc;
@@ -621,10 +624,11 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_carry_seen), 4096 * sizeof(unsigned int)));
     memset(h->h_carry_seen, 0, 4096 * sizeof(unsigned int));
   }
-  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(kItemBatch) * h->spitch, h->allocs))) return rc;
-  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(kItemBatch) * h->spitch, h->allocs))) return rc;
+  if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch = std::max(128, atoi(e));
+  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(h->item_batch) * h->spitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(h->item_batch) * h->spitch, h->allocs))) return rc;
   h->sel_pitch = (S + 63) / 64;
-  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(kItemBatch) * h->sel_pitch, h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(h->item_batch) * h->sel_pitch, h->allocs))) return rc;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
     long long min_deg = std::max<long long>(2, S / 6000);   // below ~64 listeners expanding a song on the fly is cheaper than streaming its row
@@ -836,7 +840,7 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(kItemBatch) * h->S))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(h->item_batch) * h->S))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
   return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
