@@ -152,12 +152,52 @@ head_rowsum_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__
   }
 }
 
+// IBM-only pass: the packed count rows are 2 bytes per song, so a thread takes 8 songs (one 16-byte load per row) to keep as
+// many bytes in flight per thread as the UBM pass does.
+__global__ void __launch_bounds__(256)
+head_rowsum_ibm8_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
+                        const uint32_t* __restrict__ hu_q, int u0, const uint16_t* __restrict__ g16, long long pitch, int n_songs,
+                        long long* __restrict__ sint_i, long long spitch) {
+  const int b = blockIdx.x;
+  const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
+  const int s = 8 * (blockIdx.y * blockDim.x + threadIdx.x);
+  if (s >= n_songs) return;
+  unsigned long long ia[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto add_row = [&](const uint4& c, uint32_t q, int j) {
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    const int d = j - s;                                                              // s2 != song, MR:252
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (d != 2 * t) ia[2 * t] += static_cast<unsigned long long>(w[t] & 0xffffu) * q;
+      if (d != 2 * t + 1) ia[2 * t + 1] += static_cast<unsigned long long>(w[t] >> 16) * q;
+    }
+  };
+  long long i = beg;
+  for (; i + 4 <= end; i += 4) {
+    uint4 c[4]; uint32_t q[4]; int js[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      c[t] = __ldg(reinterpret_cast<const uint4*>(g16 + static_cast<long long>(__ldg(hu_row + i + t)) * pitch + s));
+      q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) add_row(c[t], q[t], js[t]);
+  }
+  for (; i < end; ++i)
+    add_row(__ldg(reinterpret_cast<const uint4*>(g16 + static_cast<long long>(__ldg(hu_row + i)) * pitch + s)), __ldg(hu_q + i), __ldg(hu_song + i));
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch + s;
+#pragma unroll
+  for (int t = 0; t < 8; t += 2) *reinterpret_cast<ulonglong2*>(o + t) = make_ulonglong2(ia[t], ia[t + 1]);
+}
+
 int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
                        int n_users, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint_u,
                        long long* sint_i, long long spitch, cudaStream_t st) {
   if (n_users <= 0 || n_songs <= 0) return 0;
   const dim3 grid(n_users, (n_songs + 1023) / 1024);
   if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
+  else if (models == 2 && pitch % 8 == 0 && spitch % 8 == 0)
+    head_rowsum_ibm8_kernel<<<dim3(n_users, (n_songs + 2047) / 2048), 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, pitch, n_songs, sint_i, spitch);
   else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
   else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
