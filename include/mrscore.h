@@ -113,6 +113,13 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS);
 int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const double* ubm, const double* ibm, double* out,
                    int64_t n_pairs, int64_t first_index, int64_t n_total);
 
+/* evaluateModel(model) — the reference's threshold-sweep mAP (MR:521-639, 62-75 s per model on the JVM at 2000 / 100 users,
+ * README:940-944) on a materialised model: scores_UxS as mr_score_dense / mr_blend_dense produce it (NaN = pair not emitted), labels as
+ * a CSR over the same test users (rows ascending; song ids >= n_songs are label songs that occur nowhere else).  n_thresholds = 10
+ * (MR:590) or 11 (DIST:395).  Bit-identical to the CPU restatement. */
+int mr_evaluate_dense(mr_handle* h, const double* scores_UxS, int n_users, int n_songs, const int64_t* lab_rowptr, const int32_t* lab_col,
+                      int n_thresholds, double* out_map);
+
 /* getTopK(model, k): per test user the k best unlistened songs, score descending then song id ascending (new derived
  * output named by north_star; the reference has no ranking step).  out_song / out_score are U x k (song -1 / score 0.0 past
  * out_len[u] = min(k, S - |I_u|)).  1 <= k <= 1024.  model = any MR_* selector; blends are fused into the select. */

@@ -16,7 +16,7 @@ TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "preco
 
 # every symbol include/mrscore.h declares
 SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device",
-           "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_topk", "mr_topk_device",
+           "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_evaluate_dense", "mr_topk", "mr_topk_device",
            "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
 
 _lib = None
@@ -54,6 +54,7 @@ def load():
     lib.mr_similarity_ibm.argtypes = [vp, i32, i32, vp]
     lib.mr_score_dense.argtypes = [vp, i32, vp]
     lib.mr_blend_dense.argtypes = [vp, i32, dbl, u64, vp, vp, vp, i64, i64, i64]
+    lib.mr_evaluate_dense.argtypes = [vp, vp, i32, i32, vp, vp, i32, C.POINTER(dbl)]
     lib.mr_topk.argtypes = [vp, i32, dbl, u64, i32, vp, vp, vp]
     lib.mr_topk_device.argtypes = [vp, i32, dbl, u64, i32]
     lib.mr_topk_fetch.argtypes = [vp, i32, vp, vp, vp]

@@ -98,4 +98,8 @@ int launch_topk(const BlendParams& bp, const long long* sint_u, const long long*
 int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n, long long first_index,
                         cudaStream_t st);
 
+// ---- evaluation (k5_evaluate.cu)
+int launch_evaluate(const double* scores, int n_users, int n_songs, const long long* lab_ptr, const int* lab_col, const int* new_songs,
+                    int n_new, int n_thresholds, unsigned long long* minmax, double* ap_out, int num_sms, cudaStream_t st);
+
 }  // namespace mr

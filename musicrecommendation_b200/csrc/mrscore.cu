@@ -874,6 +874,45 @@ int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const do
   return MR_OK;
 }
 
+int mr_evaluate_dense(mr_handle* h, const double* scores_UxS, int n_users, int n_songs, const int64_t* lab_rowptr, const int32_t* lab_col,
+                      int n_thresholds, double* out_map) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (!scores_UxS || !lab_rowptr || !out_map || n_users <= 0 || n_songs <= 0) return fail(h, MR_ERR_BAD_ARG, "null / empty arguments");
+  if (n_thresholds != 10 && n_thresholds != 11) return fail(h, MR_ERR_BAD_ARG, "n_thresholds must be 10 (MR:590) or 11 (DIST:395)");
+  const long long n_lab = lab_rowptr[n_users];
+  if (n_lab <= 0 || !lab_col) return fail(h, MR_ERR_BAD_ARG, "empty label set");
+  for (int u = 0; u < n_users; ++u)
+    for (long long i = lab_rowptr[u] + 1; i < lab_rowptr[u + 1]; ++i)
+      if (lab_col[i] <= lab_col[i - 1]) return fail(h, MR_ERR_BAD_ARG, "label row %d not ascending/unique", u);
+  MR_CUDA(h, cudaSetDevice(h->device));
+  std::vector<int> new_songs(lab_col, lab_col + n_lab);                       // newSongs = distinct label songs (MR:72, 79)
+  std::sort(new_songs.begin(), new_songs.end());
+  new_songs.erase(std::unique(new_songs.begin(), new_songs.end()), new_songs.end());
+  const int n_new = static_cast<int>(new_songs.size());
+  std::vector<long long> lp(lab_rowptr, lab_rowptr + n_users + 1);
+  std::vector<void*> tmp;
+  double *d_scores = nullptr, *d_ap = nullptr; long long* d_lp = nullptr; int *d_lc = nullptr, *d_new = nullptr; unsigned long long* d_mm = nullptr;
+  int rc;
+  if ((rc = dev_upload(h, &d_scores, scores_UxS, static_cast<size_t>(n_users) * n_songs, tmp)) || (rc = dev_upload(h, &d_lp, lp.data(), lp.size(), tmp)) ||
+      (rc = dev_upload(h, &d_lc, lab_col, static_cast<size_t>(n_lab), tmp)) || (rc = dev_upload(h, &d_new, new_songs.data(), new_songs.size(), tmp)) ||
+      (rc = dev_alloc(h, &d_ap, static_cast<size_t>(n_new), tmp)) || (rc = dev_alloc(h, &d_mm, 2, tmp))) { free_list(tmp); return rc; }
+  int lrc;
+  {
+    PhaseTimer t(h, MR_T_OTHER);
+    lrc = launch_evaluate(d_scores, n_users, n_songs, d_lp, d_lc, d_new, n_new, n_thresholds, d_mm, d_ap, h->num_sms, h->stream);
+    h->launches += 2;
+  }
+  std::vector<double> ap(n_new);
+  cudaError_t e = lrc ? cudaErrorLaunchFailure : cudaMemcpyAsync(ap.data(), d_ap, n_new * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  free_list(tmp);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_evaluate_dense: %s", cudaGetErrorString(e));
+  double total = 0.0;
+  for (int c = 0; c < n_new; ++c) total += ap[c];                              // foldLeft(0.0)(_+_), MR:626
+  *out_map = total / n_new;
+  return MR_OK;
+}
+
 int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) {
   int rc = require_test(h);
   if (rc) return rc;

@@ -322,9 +322,15 @@ class MusicRecommender:
         return rows
 
     # ------------------------------------------------------------------ evaluation (MR:521-639), host-side like the reference
-    def evaluateModel(self, model: Model, parallel: bool = False) -> float:
-        """The reference's threshold-sweep mAP (10 thresholds, MR:590).  Runs on the host as it does in the reference."""
-        return evaluate_map(model.scores, self.ds, 10)
+    def evaluateModel(self, model: Model, parallel: bool = False, n_thresholds: int = 10) -> float:
+        """The reference's threshold-sweep mAP (MR:521-639; 10 thresholds MR:590, 11 in distributed.scala:395) on the GPU
+        (`mr_evaluate_dense`).  `evaluate_map` below is the same computation in numpy for hosts without a GPU handle."""
+        sc = np.ascontiguousarray(model.scores, np.float64)
+        lp = np.ascontiguousarray(self.ds.lab_ptr, np.int64)
+        lc = np.ascontiguousarray(self.ds.lab_col, np.int32)
+        out = C.c_double(0.0)
+        self._check(self._lib.mr_evaluate_dense(self._h, _p(sc), sc.shape[0], sc.shape[1], _p(lp), _p(lc), n_thresholds, C.byref(out)))
+        return float(out.value)
 
 
 def evaluate_map(scores: np.ndarray, ds: Dataset, n_thresholds: int = 10) -> float:

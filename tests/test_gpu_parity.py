@@ -96,7 +96,10 @@ def check_dataset(ds, oracle_lib, engine, k=500, blends=True):
                 else:
                     got = mr.getStochasticCombinationModel(ubm, ibm, param, seed=seed)
                 assert_bits_equal(got.scores, wb)
-        assert mr.evaluateModel(ubm) == pytest.approx(oracle_lib.evaluate(want["ubm"], ds), abs=1e-15)
+        # reference mAP on the GPU (MR:521-639): bit-identical to the CPU restatement, for both threshold lists
+        for nt in (10, 11):
+            assert mr.evaluateModel(ubm, n_thresholds=nt) == oracle_lib.evaluate(want["ubm"], ds, nt)
+            assert mr.evaluateModel(ibm, n_thresholds=nt) == oracle_lib.evaluate(want["ibm"], ds, nt)
         return mr.info()
 
 
@@ -180,6 +183,17 @@ def test_edge_cases(engine, oracle_lib):
         # an all-zero row ranks purely by song id
         song, _, _ = mr.getTopK(_lib.MR_UBM, k=10)
         assert song[1].tolist() == [s for s in range(11) if s != 30][:10]
+
+
+def test_evaluate_degenerate_and_blends(mrlib, oracle_lib):
+    ds = synth(T=300, U=20, S=2000, seed=1)
+    with MusicRecommender(ds) as mr:
+        ubm, ibm = mr.getUserBasedModel(), mr.getItemBasedModel()
+        for got in (mr.getLinearCombinationModel(ubm, ibm, 0.5), mr.getAggregationModel(ubm, ibm, 0.5), mr.getStochasticCombinationModel(ubm, ibm, 0.5, seed=3)):
+            assert mr.evaluateModel(got) == oracle_lib.evaluate(got.scores, ds)
+            assert mr.evaluateModel(got) == pytest.approx(evaluate_map(got.scores, ds), abs=1e-15)
+        flat = Model(np.where(ds.listened_mask(), np.nan, 0.25))          # max == min -> NaN comparisons -> no predictions -> mAP 0
+        assert mr.evaluateModel(flat) == 0.0
 
 
 def test_error_behaviour(mrlib, oracle_lib):
