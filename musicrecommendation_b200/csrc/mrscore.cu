@@ -26,10 +26,6 @@ namespace {
 
 constexpr int kSplitLen = 4096;   // listeners per K2 work item
 
-struct DevBuf {
-  void* p = nullptr; size_t bytes = 0;
-};
-
 }  // namespace
 
 struct mr_handle {

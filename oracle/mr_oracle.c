@@ -67,12 +67,6 @@ static int lin_contains(const int32_t *a, int64_t n, int32_t x) {
   return 0;
 }
 
-static int bin_contains(const int32_t *a, int64_t n, int32_t x) {
-  int64_t lo = 0, hi = n;
-  while (lo < hi) { int64_t m = (lo + hi) >> 1; if (a[m] < x) lo = m + 1; else hi = m; }
-  return lo < n && a[lo] == x;
-}
-
 /* model: 0 = UBM scale, 1 = IBM scale */
 MRO_API int64_t mro_q(int32_t deg, int model) {
   if (deg <= 0) return 0;
