@@ -167,8 +167,10 @@ __device__ __forceinline__ int prefix_cmp(unsigned long long kb, uint32_t inv, u
 
 // Stream the row: f(song, key bits, valid) is called for 4 songs per thread per iteration, the same number of times by every
 // thread of the CTA (so f may use warp collectives); valid is false for listened pairs and past the end of the row.
+// ubm_min: for the pure UBM model the score is monotone in the integer numerator, so the caller may pass the smallest numerator
+// worth looking at; rows entries below it are reported as valid with key 0 and cost no fp64 work at all.
 template <class F>
-__device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f, int chunk_stride = 1) {
+__device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f, int chunk_stride = 1, long long ubm_min = 0) {
   for (int base = 0; base < n_songs; base += 4 * kTopkThreads * chunk_stride) {
     const int s = base + 4 * static_cast<int>(threadIdx.x);
     long long a[4] = {-1, -1, -1, -1}, b[4] = {-1, -1, -1, -1};
@@ -193,7 +195,7 @@ __device__ __forceinline__ void scan_row(const KeyCtx& c, int n_songs, F&& f, in
       if (c.model != MODEL_IBM) ok = ok && a[t] >= 0;
       if (c.model != MODEL_UBM) ok = ok && b[t] >= 0;
       unsigned long long kb = 0;
-      if (ok) kb = static_cast<unsigned long long>(__double_as_longlong(
+      if (ok && (c.model != MODEL_UBM || a[t] >= ubm_min)) kb = static_cast<unsigned long long>(__double_as_longlong(
                   blend_score(c.model, a[t], b[t], c.rsu, rd[t], c.alpha, c.oma, (selw >> t) & 1ULL)));
       f(s + t, kb, ok);
     }
@@ -297,10 +299,27 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
     __syncthreads();
     const uint32_t cut = static_cast<uint32_t>(s_ctl[0]);
     __syncthreads();
+    // smallest key whose bin is >= cut (positive doubles order like their bit patterns): start at cut / scale and walk a few ulps
+    unsigned long long t_kb = 0;
+    if (cut > 0 && scale > 0.0) {
+      t_kb = static_cast<unsigned long long>(__double_as_longlong(__ddiv_rn(static_cast<double>(cut), scale)));
+      for (int i = 0; i < 64 && t_kb > 0 && bin_of(t_kb - 1) >= cut; ++i) --t_kb;
+      for (int i = 0; i < 64 && bin_of(t_kb) < cut; ++i) ++t_kb;
+    }
+    // pure UBM: the same threshold on the integer numerator (score = (double)Sint * rsu is monotone in Sint), so that the pass
+    // compares integers and only converts the handful of keys it keeps
+    long long ubm_min = 0;
+    if (c.model == MODEL_UBM && c.rsu > 0.0 && t_kb > 0) {
+      auto key_of = [&](long long v) { return static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(v), c.rsu))); };
+      ubm_min = __double2ll_rd(__ddiv_rn(__longlong_as_double(static_cast<long long>(t_kb)), c.rsu));
+      for (int i = 0; i < 64 && ubm_min > 0 && key_of(ubm_min - 1) >= t_kb; ++i) --ubm_min;
+      for (int i = 0; i < 64 && key_of(ubm_min) < t_kb; ++i) ++ubm_min;
+      if (key_of(ubm_min) < t_kb || (ubm_min > 0 && key_of(ubm_min - 1) >= t_kb)) ubm_min = 0;   // not the exact boundary: no pre-filter
+    }
     int my_valid = 0;
     scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
       my_valid += ok;
-      ok = ok && bin_of(kb) >= cut;
+      ok = ok && kb >= t_kb && (t_kb > 0 || cut == 0);
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
       if (m) {
         int base = 0;
@@ -311,7 +330,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
           if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
         }
       }
-    });
+    }, 1, ubm_min);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
     if (lane == 0) atomicAdd(&s_valid, my_valid);
