@@ -43,6 +43,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1), so fd 1 is pointed at
+# stderr for the whole run and the JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def make_workload(name: str, rank: int, world: int):
     from musicrecommendation_b200.dataset import synth_config
     t0 = time.time()
@@ -180,7 +192,7 @@ def run_reference(args, rank, world):
             "config": {"workload": desc, "k": K_TOP},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -405,7 +417,7 @@ def main():
             line["cpu_baseline_as_written"] = as_written_sample(ds) if not args.no_as_written else None
             line["cpu_baseline"] = {"value": pairs_c / sec_c, "unit": "pairs/s", "cores": thr, "kind": "port",
                                     "sample": f"first {min(args.ref_users, U)} test users of rank 0's shard, UBM+IBM canonical CPU port + top-{K_TOP}, {sec_c:.1f}s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     mr.close()
     if world > 1:
         dist.destroy_process_group()
