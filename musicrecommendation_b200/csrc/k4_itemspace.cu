@@ -13,6 +13,8 @@
 #include "mr_common.cuh"
 #include "mr_kernels.h"
 
+#include <algorithm>
+
 namespace mr {
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -52,7 +54,7 @@ int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int
   cudaError_t e = cudaMemsetAsync(g, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint32_t), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(gq, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return -1;
-  gram_head_scatter_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
+  gram_head_scatter_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);   // exits at once where a chunk has little work
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -86,7 +88,9 @@ pack_head_rows_kernel(const uint32_t* __restrict__ g, const unsigned long long* 
 int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r0, int n_rows, long long pitch, uint16_t* g16,
                           uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st) {
   if (n_rows <= 0) return 0;
-  pack_head_rows_kernel<<<num_sms * 16, 256, 0, st>>>(g, gq, r0, n_rows, pitch, g16, gq32, ex);
+  const long long n = static_cast<long long>(n_rows) * pitch;
+  const int grid = static_cast<int>(std::min<long long>(num_sms * 16LL, (n + 255) / 256));
+  pack_head_rows_kernel<<<grid, 256, 0, st>>>(g, gq, r0, n_rows, pitch, g16, gq32, ex);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
