@@ -138,7 +138,7 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 //                           most-significant-digit radix select (8-bit digits of the 96-bit key) inside the chosen bin
 // The collected keys (<= 2048) are bitonic-sorted exactly in shared memory: key descending, song ascending.
 // Every pass streams the row with 4 songs per thread (16-byte loads, 4 independent keys in flight per thread).
-constexpr int kTopkThreads = 1024;
+constexpr int kTopkThreads = 512;
 constexpr int kTopkCap = 2048;    // candidate buffer (>= 2 * k); bitonic-sorted in shared memory
 constexpr int kTopkBins = 2048;
 
@@ -216,7 +216,7 @@ __device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool ok, int l
   if ((pending >> lane) & 1u) atomicAdd(&hist[bin], 1);
 }
 
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kTopkThreads, 2)
 topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long long* __restrict__ sint_i, long long spitch,
             const uint64_t* __restrict__ sel, long long sel_pitch_words, int u0, int n_songs, const double* __restrict__ rsa,
             const double* __restrict__ rsd, int k, int* __restrict__ out_song, double* __restrict__ out_score,
