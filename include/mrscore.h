@@ -99,6 +99,15 @@ int mr_counts_ibm(mr_handle* h, int s0, int s1, int32_t* out_rows);
  * partial panels of all ranks with one NCCL reduce-scatter.  The pointer is valid until the next call on the handle. */
 int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t* ld);
 
+/* The same with the reduce-scatter FUSED into the count GEMM: the epilogue stores every output row straight into the receive slot of
+ * the rank that owns it — slot_ptrs[m / rows_per_owner] + (m % rows_per_owner) * ld, int32 — which may be this GPU's memory or a
+ * peer's HBM mapped over NVLink (mr_peer_alloc / mr_peer_open, CUDA IPC), in coalesced 128-byte row segments, tile by tile while the
+ * tensor cores work on the next tile.  The owner then sums its `world` slots locally (integers: exact).  Tensor engine only. */
+int mr_gram_rows_scatter(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld);
+int mr_peer_alloc(mr_handle* h, uint64_t bytes, void** dev_ptr, unsigned char* handle_out_64);   /* zeroed device buffer + its IPC handle */
+int mr_peer_open(mr_handle* h, const unsigned char* handle_64, void** dev_ptr);                  /* map a peer's buffer into this process */
+int mr_peer_close(mr_handle* h, void* dev_ptr);
+
 /* Cosine similarities with the normalisation fused into the GEMM epilogue (fp32): user-user MR:140-149 and rows [s0,s1) of
  * item-item MR:230-239 (denominator uses the train+test listener counts, MR:237). */
 int mr_similarity_ubm(mr_handle* h, float* out_UxT);

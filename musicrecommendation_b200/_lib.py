@@ -15,7 +15,7 @@ MR_SPACE_AUTO, MR_SPACE_USER, MR_SPACE_ITEM = 0, 8, 16
 TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
 
 # every symbol include/mrscore.h declares
-SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device",
+SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device", "mr_gram_rows_scatter", "mr_peer_alloc", "mr_peer_open", "mr_peer_close",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_evaluate_dense", "mr_topk", "mr_topk_device",
            "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
 
@@ -50,6 +50,10 @@ def load():
     lib.mr_counts_ubm.argtypes = [vp, vp]
     lib.mr_counts_ibm.argtypes = [vp, i32, i32, vp]
     lib.mr_gram_rows_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
+    lib.mr_gram_rows_scatter.argtypes = [vp, i32, i32, C.POINTER(vp), i32, i32, i64]
+    lib.mr_peer_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
+    lib.mr_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.mr_peer_close.argtypes = [vp, vp]
     lib.mr_similarity_ubm.argtypes = [vp, vp]
     lib.mr_similarity_ibm.argtypes = [vp, i32, i32, vp]
     lib.mr_score_dense.argtypes = [vp, i32, vp]

@@ -15,6 +15,8 @@
 //   EPI_I32      int32 C row-major                      (parity probes mr_counts_*, Gram rows consumed by the IBM aggregation)
 //   EPI_U16_T    uint16 C^T  (Ct[n][m], m contiguous)   (UBM: train-user-major count panel consumed by the K2 gather)
 //   EPI_COS_F32  float   C[m][n] / (sqrt(da[m]) * sqrt(db[n]))   fused cosine normalisation (similarity products, MR:147-148 / 237-238)
+//   EPI_I32_SCATTER  int32 rows stored into per-owner receive slots (local or NVLink peer memory): the reduce-scatter of the K-split
+//                item-item sweep fused into the epilogue (coalesced 128-byte row segments via a shared-memory transpose)
 //   EPI_ACC_U64  u64 out (+)= C << shift                         byte-plane accumulation of the weighted Gram Gq (item-space head rows)
 #include "mr_common.cuh"
 #include "mr_kernels.h"
@@ -36,7 +38,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTransposeBytes = 4 * 32 * 33 * 4;   // per epilogue warp a padded 32x32 int32 tile (EPI_I32_SCATTER)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kTransposeBytes;
 };
 
 struct GemmParams {
@@ -47,6 +50,8 @@ struct GemmParams {
   long long ld;        // leading dimension of `out` in elements
   const float* rsa;    // EPI_COS_F32: 1/sqrt(deg) per A row, per B row (0 where deg == 0)
   const float* rsb;
+  int32_t* slots[8];   // EPI_I32_SCATTER: row m goes to slots[m / rows_per_owner] + (m % rows_per_owner) * ld  (peer or local memory)
+  int rows_per_owner;
   int shift;           // EPI_ACC_U64: out = (plane 0 ? 0 : out) + (u64(acc) << shift)  (byte-plane weighted Gram)
   int accumulate;
 };
@@ -66,6 +71,7 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;            // [2]        epilogue -> MMA
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int32_t* tr_smem = reinterpret_cast<int32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [4 warps][32][33]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,6 +166,26 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 32 && n0 + j < p.N; ++j) dst[j] = (int)r[j];
             }
           }
+        } else if constexpr (EPI == EPI_I32_SCATTER) {
+          // Reduce-scatter fused into the GEMM: every output row is stored straight into the receive slot of the rank that owns
+          // it (its own HBM or a peer's over NVLink, IPC-mapped).  The 32x32 block is transposed through shared memory so that
+          // each store instruction writes 128 contiguous bytes of ONE row — full NVLink / HBM packets instead of 32 slivers.
+          int32_t* tile = tr_smem + q * (32 * 33);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = static_cast<int32_t>(r[j]);
+          __syncwarp();
+          const int m_base = m_tile * kBM + q * 32;
+          if (n0 + lane < p.N) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int mm = m_base + rr;
+              if (mm < p.M) {
+                const int o = mm / p.rows_per_owner;
+                p.slots[o][static_cast<long long>(mm - o * p.rows_per_owner) * p.ld + n0 + lane] = tile[rr * 33 + lane];
+              }
+            }
+          }
+          __syncwarp();
         } else if constexpr (EPI == EPI_U16_T) {
           // Ct[n][m] (p.ld = 128): the 32 lanes of a warp hold 32 consecutive m -> one 64-byte store per column n
           if (m < kUserBatch) {
@@ -298,7 +324,7 @@ static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, c
 
 int launch_count_gemm(const uint8_t* A, long long a_rows, const uint8_t* B, long long b_rows, long long pitch, int M, int N,
                       int epi, void* out, long long ld, const float* rsa, const float* rsb, int num_sms, cudaStream_t st,
-                      int shift, int accumulate) {
+                      int shift, int accumulate, int32_t* const* slots, int n_slots, int rows_per_owner) {
   if (pitch % kBK != 0 || M <= 0 || N <= 0) return -3;
   const int bn = (N > 128) ? 256 : 128;
   CUtensorMap ta, tb;
@@ -312,16 +338,21 @@ int launch_count_gemm(const uint8_t* A, long long a_rows, const uint8_t* B, long
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;
   p.out = out; p.ld = ld; p.rsa = rsa; p.rsb = rsb; p.shift = shift; p.accumulate = accumulate;
+  for (int i = 0; i < 8; ++i) p.slots[i] = (slots && i < n_slots) ? slots[i] : nullptr;
+  p.rows_per_owner = rows_per_owner > 0 ? rows_per_owner : 1;
+  if (epi == EPI_I32_SCATTER && (!slots || n_slots < 1 || n_slots > 8 || static_cast<long long>(n_slots) * p.rows_per_owner < M)) return -4;
   cudaError_t e;
   if (bn == 256) {
     e = epi == EPI_I32 ? launch_gemm_t<256, EPI_I32>(ta, tb, p, num_sms, st)
       : epi == EPI_U16_T ? launch_gemm_t<256, EPI_U16_T>(ta, tb, p, num_sms, st)
       : epi == EPI_ACC_U64 ? launch_gemm_t<256, EPI_ACC_U64>(ta, tb, p, num_sms, st)
+      : epi == EPI_I32_SCATTER ? launch_gemm_t<256, EPI_I32_SCATTER>(ta, tb, p, num_sms, st)
                          : launch_gemm_t<256, EPI_COS_F32>(ta, tb, p, num_sms, st);
   } else {
     e = epi == EPI_I32 ? launch_gemm_t<128, EPI_I32>(ta, tb, p, num_sms, st)
       : epi == EPI_U16_T ? launch_gemm_t<128, EPI_U16_T>(ta, tb, p, num_sms, st)
       : epi == EPI_ACC_U64 ? launch_gemm_t<128, EPI_ACC_U64>(ta, tb, p, num_sms, st)
+      : epi == EPI_I32_SCATTER ? launch_gemm_t<128, EPI_I32_SCATTER>(ta, tb, p, num_sms, st)
                          : launch_gemm_t<128, EPI_COS_F32>(ta, tb, p, num_sms, st);
   }
   return e == cudaSuccess ? 0 : -100 - static_cast<int>(e);

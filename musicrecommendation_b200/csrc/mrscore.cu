@@ -839,6 +839,75 @@ int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t
   return MR_OK;
 }
 
+int mr_peer_alloc(mr_handle* h, uint64_t bytes, void** dev_ptr, unsigned char* handle_out_64) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (!dev_ptr || !handle_out_64 || bytes == 0) return fail(h, MR_ERR_BAD_ARG, "null output / zero size");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  void* p = nullptr;
+  MR_CUDA(h, cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(h, MR_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out_64, &hd, 64);
+  MR_CUDA(h, cudaMemsetAsync(p, 0, bytes, h->stream));
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->allocs.push_back(p);
+  h->dev_bytes += bytes;
+  *dev_ptr = p;
+  return MR_OK;
+}
+
+int mr_peer_open(mr_handle* h, const unsigned char* handle_64, void** dev_ptr) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (!dev_ptr || !handle_64) return fail(h, MR_ERR_BAD_ARG, "null argument");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle_64, 64);
+  MR_CUDA(h, cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return MR_OK;
+}
+
+int mr_peer_close(mr_handle* h, void* dev_ptr) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  MR_CUDA(h, cudaSetDevice(h->device));
+  MR_CUDA(h, cudaIpcCloseMemHandle(dev_ptr));
+  return MR_OK;
+}
+
+int mr_gram_rows_scatter(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  if (h->engine != MR_ENGINE_TENSOR) return fail(h, MR_ERR_STATE, "mr_gram_rows_scatter needs the tensor engine (the scatter is the GEMM epilogue)");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  if (s0 < 0 || s1 > h->S || s0 >= s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
+  const int n = s1 - s0;
+  if (!slot_ptrs || n_owners < 1 || n_owners > 8 || rows_per_owner < 1 || static_cast<long long>(n_owners) * rows_per_owner < n || ld < h->S)
+    return fail(h, MR_ERR_BAD_ARG, "bad slot table (owners %d, rows per owner %d, ld %lld)", n_owners, rows_per_owner, static_cast<long long>(ld));
+  const int rows_pad = static_cast<int>(round_up(n, 128));
+  const size_t need_a = static_cast<size_t>(rows_pad) * h->pitchT;
+  if (need_a > h->aj_bytes) {
+    uint8_t* pa; int rc = dev_alloc(h, &pa, need_a, h->allocs);
+    if (rc) return rc;
+    h->d_Aj = pa; h->aj_bytes = need_a;
+  }
+  int* d_ids = nullptr;
+  int rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_GRAM_IDS, &d_ids, static_cast<size_t>(n)))) return rc;
+  iota_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_ids, s0, n);
+  h->launches++;
+  {
+    PhaseTimer t(h, MR_T_EXPAND);
+    MR_LAUNCH(h, launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, d_ids, 0, n, rows_pad, h->pitchT, h->d_Aj, h->stream));
+  }
+  int32_t* slots[8];
+  for (int i = 0; i < n_owners; ++i) slots[i] = static_cast<int32_t*>(slot_ptrs[i]);
+  PhaseTimer t(h, MR_T_COUNT);
+  MR_LAUNCH(h, launch_count_gemm(h->d_Aj, rows_pad, h->d_AtrT, h->S, h->pitchT, n, h->S, EPI_I32_SCATTER, nullptr, ld, nullptr, nullptr, h->num_sms,
+                                 h->stream, 0, 0, slots, n_owners, rows_per_owner));
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MR_OK;
+}
+
 int mr_counts_ibm(mr_handle* h, int s0, int s1, int32_t* out_rows) {
   if (!out_rows) return fail(h, MR_ERR_BAD_ARG, "null output");
   return gram_range(h, s0, s1, out_rows, nullptr);

@@ -277,6 +277,27 @@ class MusicRecommender:
             __cuda_array_interface__ = {"shape": (s1 - s0, ld.value), "typestr": "<i4", "data": (ptr.value, False), "version": 2}
         return torch.as_tensor(_Arr(), device="cuda")
 
+    # ---- fused K-split reduce-scatter (GEMM epilogue stores into the owners' receive slots, local or NVLink peer memory)
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte CUDA IPC handle) of a zeroed buffer other ranks can map with peer_open."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._check(self._lib.mr_peer_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.mr_peer_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self._check(self._lib.mr_peer_close(self._h, C.c_void_p(ptr)))
+
+    def gram_rows_scatter(self, s0: int, s1: int, slot_ptrs, rows_per_owner: int, ld: int):
+        arr = (C.c_void_p * len(slot_ptrs))(*slot_ptrs)
+        self._check(self._lib.mr_gram_rows_scatter(self._h, s0, s1, arr, len(slot_ptrs), rows_per_owner, ld))
+
     def similarity_ubm(self) -> np.ndarray:
         out = np.empty((self.ds.U, self.ds.T), np.float32)
         self._check(self._lib.mr_similarity_ubm(self._h, _p(out)))
