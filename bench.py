@@ -322,7 +322,7 @@ def main():
     phases = mr.timing()
     lib.mr_set_profile(h, 0)
     info = mr.info()
-    batch = 1184 if info["space"] == _lib.MR_SPACE_ITEM else 128    # kItemBatch / kUserBatch
+    batch = int(info["batch_rows"]) if info["space"] == _lib.MR_SPACE_ITEM else 128    # test users per batch (mr_get_info) / kUserBatch
     n_batches = (U + batch - 1) // batch
 
     # max over ranks
@@ -392,8 +392,8 @@ def main():
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
             "config": {"workload": desc, "k": K_TOP, "engine": ["auto", "tensor", "sparse"][info["engine"]],
-                       "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"],
-                       "l2": "inputs (precomputed head rows >= 10 GB, train CSR/CSC 0.7 GB, 0.8 GB of Sint panels per batch) exceed the 126 MB L2; no explicit flush",
+                       "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"], "users_per_batch": batch,
+                       "l2": "inputs (precomputed head rows >= 10 GB, train CSR/CSC 0.7 GB, the Sint panel of a batch: 8 B per (user, song)) exceed the 126 MB L2; no explicit flush",
                        "pairs_per_step": pairs_all, "precompute_ms_once_per_train_set": precompute_ms},
             "e2e": {"value": pairs_all * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps},

@@ -148,7 +148,8 @@ int mr_get_timing(mr_handle* h, double* ms_out, int n);      /* accumulated CUDA
 int mr_reset_timing(mr_handle* h);
 int mr_set_profile(mr_handle* h, int on);                   /* toggle MR_PROFILE at run time (it synchronises after every phase) */
 int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated, space, n_head songs,
-                                                                 test entries on head songs, test entries on tail songs] */
+                                                                 test entries on head songs, test entries on tail songs, head-row exceptions,
+                                                                 test users per batch, head_rowsum work groups per batch, users split over groups] */
 void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
 
 #ifdef __cplusplus

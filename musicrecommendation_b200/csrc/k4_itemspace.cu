@@ -95,115 +95,112 @@ int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Head part of a batch: Sint[b][s] = sum over the user's head entries of the precomputed (packed) rows.  Thread = (user b,
-// 4 songs); every row read is a coalesced 8-byte (4 x u16 of G) or 16-byte (4 x u32 of Gq) vector load along the song axis;
-// 4 rows are kept in flight.  kModels: 1 = UBM only, 2 = IBM only, 3 = both.
+// Head part of a batch: Sint[b][s] = sum over the user's head entries of the precomputed (packed) rows.
+//
+// HBM-bandwidth bound, and most of the gathered bytes are rows of popular songs that many users of the batch share, so the kernel
+// is organised for L2 reuse: the grid is (group, song tile) with the group index fastest and exactly as many groups as CTAs fit on
+// the GPU, i.e. one wave of CTAs = one song tile.  A group is a list of work segments (user, range of its head entries) that the
+// host balanced to equal length (longest-processing-time packing; users with more entries than a group's share are split into
+// several segments that accumulate with atomics into a pre-zeroed row).  Equal work keeps all resident CTAs on the same song tile
+// at the same time, so a row tile is fetched from HBM once and served from L2 to every other user that needs it — the DRAM traffic
+// of a pass approaches "each distinct head row of the batch once + the Sint rows written".
+// Thread = kVec consecutive songs; every row read is one coalesced vector load along the song axis (4 x u32 of Gq32 / 8 x u16 of
+// G16 at the widest), several rows in flight per thread.  Sint is written with streaming stores (it is re-read only by top-k, long
+// after it has left L2).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kModels>
-__global__ void __launch_bounds__(256)
-head_rowsum_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
-                   const uint32_t* __restrict__ hu_q, int u0, const uint16_t* __restrict__ g16, const uint32_t* __restrict__ gq32,
-                   long long pitch, int n_songs, long long* __restrict__ sint_u, long long* __restrict__ sint_i, long long spitch) {
-  // blockIdx.x = user, blockIdx.y = song tile: CTAs that are resident together work on the SAME song tile for different users, so
-  // the row tiles of popular songs (shared by many users of the batch) are fetched from HBM once and hit in L2 for the others
-  const int b = blockIdx.x;
-  const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
-  const int s = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+template <int W> struct RowWords { uint32_t w[W]; };
+template <int W> __device__ __forceinline__ RowWords<W> ld_row_words(const void* p);
+template <> __device__ __forceinline__ RowWords<1> ld_row_words<1>(const void* p) { RowWords<1> r; r.w[0] = __ldg(static_cast<const uint32_t*>(p)); return r; }
+template <> __device__ __forceinline__ RowWords<2> ld_row_words<2>(const void* p) {
+  const uint2 v = __ldg(static_cast<const uint2*>(p)); RowWords<2> r; r.w[0] = v.x; r.w[1] = v.y; return r;
+}
+template <> __device__ __forceinline__ RowWords<4> ld_row_words<4>(const void* p) {
+  const uint4 v = __ldg(static_cast<const uint4*>(p)); RowWords<4> r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w; return r;
+}
+
+// kIbm = false: UBM pass over Gq32 (W songs per thread).  kIbm = true: IBM pass over G16 (2 W songs per thread, weight qd[j] per row,
+// the entry s == j excluded: `s2 != song`, MusicRecommender.scala:252).
+template <bool kIbm, int W>
+__global__ void __launch_bounds__(256, kIbm ? kHeadCtasPerSm / 2 : kHeadCtasPerSm)
+head_rowsum_kernel(const int* __restrict__ grp_ptr, const int4* __restrict__ seg, const int* __restrict__ hu_row,
+                   const int* __restrict__ hu_song, const uint32_t* __restrict__ hu_q, const uint16_t* __restrict__ g16,
+                   const uint32_t* __restrict__ gq32, long long pitch, int n_songs, long long* __restrict__ sint, long long spitch) {
+  constexpr int kVec = kIbm ? 2 * W : W;
+  constexpr int kRows = W == 4 ? 4 : 8;                       // rows in flight per thread
+  const int s = kVec * (blockIdx.y * blockDim.x + threadIdx.x);
   if (s >= n_songs) return;
-  unsigned long long ua[4] = {0, 0, 0, 0}, ia[4] = {0, 0, 0, 0};
-  long long i = beg;
-  for (; i + 4 <= end; i += 4) {
-    uint4 cu[4]; uint2 ci[4]; uint32_t q[4]; int js[4];
+  const char* base = kIbm ? reinterpret_cast<const char*>(g16 + s) : reinterpret_cast<const char*>(gq32 + s);
+  const long long row_bytes = pitch * (kIbm ? 2 : 4);
+  for (int gi = __ldg(grp_ptr + blockIdx.x), ge = __ldg(grp_ptr + blockIdx.x + 1); gi < ge; ++gi) {
+    const int4 sg = __ldg(seg + gi);                          // x: Sint row, y..z: head entries, w: accumulate into a pre-zeroed row
+    unsigned long long acc[kVec];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const long long row = static_cast<long long>(__ldg(hu_row + i + t)) * pitch + s;
-      if (kModels & 1) cu[t] = __ldg(reinterpret_cast<const uint4*>(gq32 + row));
-      if (kModels & 2) { ci[t] = __ldg(reinterpret_cast<const uint2*>(g16 + row)); q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); }
-    }
+    for (int t = 0; t < kVec; ++t) acc[t] = 0;
+    auto add_row = [&](const RowWords<W>& c, uint32_t q, int j) {
+      if (!kIbm) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (kModels & 1) { ua[0] += cu[t].x; ua[1] += cu[t].y; ua[2] += cu[t].z; ua[3] += cu[t].w; }
-      if (kModels & 2) {
-        const uint32_t c0 = ci[t].x & 0xffffu, c1 = ci[t].x >> 16, c2 = ci[t].y & 0xffffu, c3 = ci[t].y >> 16;
-        const int d = js[t] - s;                                                          // s2 != song, MR:252
-        if (d != 0) ia[0] += static_cast<unsigned long long>(c0) * q[t];
-        if (d != 1) ia[1] += static_cast<unsigned long long>(c1) * q[t];
-        if (d != 2) ia[2] += static_cast<unsigned long long>(c2) * q[t];
-        if (d != 3) ia[3] += static_cast<unsigned long long>(c3) * q[t];
+        for (int t = 0; t < W; ++t) acc[t] += c.w[t];
+      } else {
+        const int d = j - s;
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+          if (d != 2 * t) acc[2 * t] += static_cast<unsigned long long>(c.w[t] & 0xffffu) * q;
+          if (d != 2 * t + 1) acc[2 * t + 1] += static_cast<unsigned long long>(c.w[t] >> 16) * q;
+        }
       }
+    };
+    int i = sg.y;
+    for (; i + kRows <= sg.z; i += kRows) {
+      RowWords<W> c[kRows]; uint32_t q[kRows]; int js[kRows];
+#pragma unroll
+      for (int t = 0; t < kRows; ++t) {
+        c[t] = ld_row_words<W>(base + static_cast<long long>(__ldg(hu_row + i + t)) * row_bytes);
+        if (kIbm) { q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); } else { q[t] = 0; js[t] = 0; }
+      }
+#pragma unroll
+      for (int t = 0; t < kRows; ++t) add_row(c[t], q[t], js[t]);
     }
-  }
-  for (; i < end; ++i) {
-    const long long row = static_cast<long long>(__ldg(hu_row + i)) * pitch + s;
-    if (kModels & 1) { const uint4 c = __ldg(reinterpret_cast<const uint4*>(gq32 + row)); ua[0] += c.x; ua[1] += c.y; ua[2] += c.z; ua[3] += c.w; }
-    if (kModels & 2) {
-      const uint2 c = __ldg(reinterpret_cast<const uint2*>(g16 + row));
-      const uint32_t q = __ldg(hu_q + i); const int d = __ldg(hu_song + i) - s;
-      if (d != 0) ia[0] += static_cast<unsigned long long>(c.x & 0xffffu) * q;
-      if (d != 1) ia[1] += static_cast<unsigned long long>(c.x >> 16) * q;
-      if (d != 2) ia[2] += static_cast<unsigned long long>(c.y & 0xffffu) * q;
-      if (d != 3) ia[3] += static_cast<unsigned long long>(c.y >> 16) * q;
+    for (; i < sg.z; ++i)
+      add_row(ld_row_words<W>(base + static_cast<long long>(__ldg(hu_row + i)) * row_bytes), kIbm ? __ldg(hu_q + i) : 0u, kIbm ? __ldg(hu_song + i) : 0);
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(sint) + static_cast<long long>(sg.x) * spitch + s;
+    if (sg.w) {
+#pragma unroll
+      for (int t = 0; t < kVec; ++t) if (acc[t]) atomicAdd(o + t, acc[t]);
+    } else if (kVec == 1) {
+      __stcs(o, acc[0]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < kVec; t += 2) __stcs(reinterpret_cast<ulonglong2*>(o + t), make_ulonglong2(acc[t], acc[t + 1]));
     }
-  }
-  const long long o = static_cast<long long>(b) * spitch + s;
-  if (kModels & 1) {
-    *reinterpret_cast<ulonglong2*>(sint_u + o) = make_ulonglong2(ua[0], ua[1]);
-    *reinterpret_cast<ulonglong2*>(sint_u + o + 2) = make_ulonglong2(ua[2], ua[3]);
-  }
-  if (kModels & 2) {
-    *reinterpret_cast<ulonglong2*>(sint_i + o) = make_ulonglong2(ia[0], ia[1]);
-    *reinterpret_cast<ulonglong2*>(sint_i + o + 2) = make_ulonglong2(ia[2], ia[3]);
   }
 }
 
-// IBM-only pass: the packed count rows are 2 bytes per song, so a thread takes 8 songs (one 16-byte load per row) to keep as
-// many bytes in flight per thread as the UBM pass does.
+int head_rowsum_tile_songs(int model, int words) { return 256 * (model == 2 ? 2 * words : words); }
+
+int launch_head_rowsum(int model, int words, const int* grp_ptr, int n_groups, const int4* seg, const int* hu_row, const int* hu_song,
+                       const uint32_t* hu_q, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint,
+                       long long spitch, cudaStream_t st) {
+  if (n_groups <= 0 || n_songs <= 0) return 0;
+  const int tile = head_rowsum_tile_songs(model, words);
+  const dim3 grid(n_groups, (n_songs + tile - 1) / tile);
+#define MR_HR(IBM, W) head_rowsum_kernel<IBM, W><<<grid, 256, 0, st>>>(grp_ptr, seg, hu_row, hu_song, hu_q, g16, gq32, pitch, n_songs, sint, spitch)
+  if (model == 1) { if (words == 4) MR_HR(false, 4); else if (words == 2) MR_HR(false, 2); else if (words == 1) MR_HR(false, 1); else return -2; }
+  else if (model == 2) { if (words == 4) MR_HR(true, 4); else if (words == 2) MR_HR(true, 2); else if (words == 1) MR_HR(true, 1); else return -2; }
+  else return -2;
+#undef MR_HR
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// rows of users whose head entries were split over several segments start from zero (the segments accumulate atomically)
 __global__ void __launch_bounds__(256)
-head_rowsum_ibm8_kernel(const long long* __restrict__ hu_ptr, const int* __restrict__ hu_row, const int* __restrict__ hu_song,
-                        const uint32_t* __restrict__ hu_q, int u0, const uint16_t* __restrict__ g16, long long pitch, int n_songs,
-                        long long* __restrict__ sint_i, long long spitch) {
-  const int b = blockIdx.x;
-  const long long beg = hu_ptr[u0 + b], end = hu_ptr[u0 + b + 1];
-  const int s = 8 * (blockIdx.y * blockDim.x + threadIdx.x);
-  if (s >= n_songs) return;
-  unsigned long long ia[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto add_row = [&](const uint4& c, uint32_t q, int j) {
-    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-    const int d = j - s;                                                              // s2 != song, MR:252
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (d != 2 * t) ia[2 * t] += static_cast<unsigned long long>(w[t] & 0xffffu) * q;
-      if (d != 2 * t + 1) ia[2 * t + 1] += static_cast<unsigned long long>(w[t] >> 16) * q;
-    }
-  };
-  long long i = beg;
-  for (; i + 4 <= end; i += 4) {
-    uint4 c[4]; uint32_t q[4]; int js[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      c[t] = __ldg(reinterpret_cast<const uint4*>(g16 + static_cast<long long>(__ldg(hu_row + i + t)) * pitch + s));
-      q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) add_row(c[t], q[t], js[t]);
-  }
-  for (; i < end; ++i)
-    add_row(__ldg(reinterpret_cast<const uint4*>(g16 + static_cast<long long>(__ldg(hu_row + i)) * pitch + s)), __ldg(hu_q + i), __ldg(hu_song + i));
-  unsigned long long* o = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch + s;
-#pragma unroll
-  for (int t = 0; t < 8; t += 2) *reinterpret_cast<ulonglong2*>(o + t) = make_ulonglong2(ia[t], ia[t + 1]);
+zero_rows_kernel(const int* __restrict__ rows, long long* __restrict__ sint, long long spitch) {
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(sint + static_cast<long long>(rows[blockIdx.x]) * spitch);
+  for (long long i = blockIdx.y * blockDim.x + threadIdx.x; i < spitch / 2; i += static_cast<long long>(gridDim.y) * blockDim.x) o[i] = make_ulonglong2(0, 0);
 }
 
-int launch_head_rowsum(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0,
-                       int n_users, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint_u,
-                       long long* sint_i, long long spitch, cudaStream_t st) {
-  if (n_users <= 0 || n_songs <= 0) return 0;
-  const dim3 grid(n_users, (n_songs + 1023) / 1024);
-  if (models == 1) head_rowsum_kernel<1><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
-  else if (models == 2 && pitch % 8 == 0 && spitch % 8 == 0)
-    head_rowsum_ibm8_kernel<<<dim3(n_users, (n_songs + 2047) / 2048), 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, pitch, n_songs, sint_i, spitch);
-  else if (models == 2) head_rowsum_kernel<2><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
-  else head_rowsum_kernel<3><<<grid, 256, 0, st>>>(hu_ptr, hu_row, hu_song, hu_q, u0, g16, gq32, pitch, n_songs, sint_u, sint_i, spitch);
+int launch_zero_rows(const int* rows, int n_rows, long long* sint, long long spitch, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  zero_rows_kernel<<<dim3(n_rows, 64), 256, 0, st>>>(rows, sint, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

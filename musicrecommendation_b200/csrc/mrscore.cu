@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <queue>
 #include <vector>
 
 using namespace mr;
@@ -44,7 +45,11 @@ struct mr_handle {
   long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
   uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
   // item-space engine: head songs and their precomputed rows
-  int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false; int item_batch = kItemBatch;
+  int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false;
+  int item_batch_cap = 0;              // MRSCORE_ITEM_BATCH: upper bound on test users per item-space batch (0 = as many as fit in HBM)
+  int batch_rows = kUserBatch;         // test users per batch of the current shard = rows of the Sint panels
+  int head_words_u = 4, head_words_i = 4, n_groups = 0;   // head_rowsum: 32-bit words per row load (UBM / IBM pass), groups per batch
+  int4* d_seg = nullptr; int* d_grp_ptr = nullptr; int* d_split_rows = nullptr; std::vector<int> h_split_ptr;   // balanced work groups per batch
   std::vector<int> head_index;         // song -> head row or -1
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
   long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
@@ -54,7 +59,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_SEG, SL_GRP_PTR, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -111,11 +116,11 @@ int dev_alloc(mr_handle* h, Tp** out, size_t count, std::vector<void*>& owner) {
 }
 
 template <class Tp>
-int slot_alloc(mr_handle* h, int slot, Tp** out, size_t count) {
+int slot_alloc(mr_handle* h, int slot, Tp** out, size_t count, bool exact = false) {
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
   if (h->slot_cap[slot] < bytes) {
     if (h->slot_p[slot]) { cudaFree(h->slot_p[slot]); h->dev_bytes -= h->slot_cap[slot]; h->slot_p[slot] = nullptr; h->slot_cap[slot] = 0; }
-    const size_t cap = bytes + bytes / 4 + 256;
+    const size_t cap = exact ? bytes : bytes + bytes / 4 + 256;
     void* p = nullptr;
     MR_CUDA(h, cudaMalloc(&p, cap));
     h->slot_p[slot] = p; h->slot_cap[slot] = cap; h->dev_bytes += cap;
@@ -378,6 +383,77 @@ int ensure_head_rows(mr_handle* h) {
   return MR_OK;
 }
 
+// Batch plan of the current test shard.  User space: 128-user batches (UMMA M).  Item space: as many test users per batch as the Sint
+// panels (two models, 8 bytes per (user, song)) fit in HBM next to the head rows — a large batch shares the row tiles of popular
+// songs among more users (head_rowsum_kernel) — split evenly, plus per batch the balanced work groups of head_rowsum_kernel:
+// segments (Sint row, head-entry range) packed longest-first into n_groups bins of equal total length.
+int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
+  int rc;
+  const int U = h->U;
+  h->batch_rows = kUserBatch;
+  if (h->space == MR_SPACE_ITEM) {
+    size_t free_b = 0, total_b = 0;
+    MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_row = static_cast<size_t>(h->spitch) * 16 + static_cast<size_t>(h->sel_pitch) * 8;
+    size_t avail = free_b + h->slot_cap[mr_handle::SL_SINT_U] + h->slot_cap[mr_handle::SL_SINT_I] + h->slot_cap[mr_handle::SL_SEL];
+    size_t reserve = (3ULL << 30) + static_cast<size_t>(kDenseChunk) * h->S * 8;
+    if (!h->head_ready) reserve += static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch * 6 + (1ULL << 30);   // head rows + staging come later
+    long long max_rows = avail > reserve ? static_cast<long long>((avail - reserve) / per_row) : 0;
+    max_rows = std::max<long long>(max_rows, kUserBatch);
+    if (h->item_batch_cap > 0) max_rows = std::min<long long>(max_rows, h->item_batch_cap);
+    const int n_batches = static_cast<int>((U + max_rows - 1) / max_rows);
+    h->batch_rows = std::max(kUserBatch, (U + n_batches - 1) / n_batches);
+  }
+  const size_t rows = static_cast<size_t>(h->batch_rows);
+  if ((rc = slot_alloc(h, mr_handle::SL_SINT_U, &h->d_sint_u, rows * h->spitch, true))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_SINT_I, &h->d_sint_i, rows * h->spitch, true))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_SEL, &h->d_sel, rows * h->sel_pitch, true))) return rc;
+  if (h->space != MR_SPACE_ITEM) return MR_OK;
+
+  const int G = h->n_groups, B = h->batch_rows;
+  const int n_batches = (U + B - 1) / B;
+  std::vector<int4> seg; std::vector<int> grp_ptr; std::vector<int> split_rows;
+  h->h_split_ptr.assign(1, 0);
+  struct Item { int row, e0, e1, acc; };
+  std::vector<Item> items; std::vector<std::vector<int>> bins(G);
+  for (int bi = 0; bi < n_batches; ++bi) {
+    const int b0 = bi * B, nb = std::min(B, U - b0);
+    const long long entries = hu_ptr[b0 + nb] - hu_ptr[b0];
+    // a segment costs its entries plus ~3 entry-equivalents for the Sint row it writes (8 B/song against 4 or 2 B/song per entry)
+    constexpr int kRowCost = 3;
+    const long long share = (entries + static_cast<long long>(kRowCost) * nb + G - 1) / G;
+    const int cap = static_cast<int>(std::max<long long>(32, share));
+    items.clear();
+    for (int b = 0; b < nb; ++b) {
+      const int e0 = static_cast<int>(hu_ptr[b0 + b]), e1 = static_cast<int>(hu_ptr[b0 + b + 1]), n = e1 - e0;
+      if (n <= cap) { items.push_back({b, e0, e1, 0}); continue; }
+      const int parts = (n + cap - 1) / cap;
+      for (int p = 0; p < parts; ++p) items.push_back({b, e0 + static_cast<int>(static_cast<long long>(n) * p / parts), e0 + static_cast<int>(static_cast<long long>(n) * (p + 1) / parts), 1});
+      split_rows.push_back(b);
+    }
+    h->h_split_ptr.push_back(static_cast<int>(split_rows.size()));
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.e1 - a.e0 > b.e1 - b.e0; });
+    for (auto& v : bins) v.clear();
+    std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> heap;
+    for (int g = 0; g < G; ++g) heap.push({0, g});
+    for (size_t i = 0; i < items.size(); ++i) {
+      auto top = heap.top(); heap.pop();
+      bins[top.second].push_back(static_cast<int>(i));
+      heap.push({top.first + (items[i].e1 - items[i].e0) + kRowCost, top.second});
+    }
+    for (int g = 0; g < G; ++g) {
+      grp_ptr.push_back(static_cast<int>(seg.size()));
+      for (int i : bins[g]) seg.push_back(make_int4(items[i].row, items[i].e0, items[i].e1, items[i].acc));
+    }
+    grp_ptr.push_back(static_cast<int>(seg.size()));
+  }
+  if ((rc = slot_upload(h, mr_handle::SL_SEG, &h->d_seg, seg.data(), seg.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_GRP_PTR, &h->d_grp_ptr, grp_ptr.data(), grp_ptr.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_SPLIT_ROWS, &h->d_split_rows, split_rows.data(), split_rows.size()))) return rc;
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging vectors above are pageable and go out of scope
+  return MR_OK;
+}
+
 enum RunMode { RUN_TOPK, RUN_DENSE, RUN_COUNTS_UBM, RUN_SIM_UBM };
 
 int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode mode, void* host_out) {
@@ -385,15 +461,26 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
   const bool need_ibm = model != MODEL_UBM && mode != RUN_COUNTS_UBM && mode != RUN_SIM_UBM;
   const bool item_space = h->space == MR_SPACE_ITEM && (mode == RUN_TOPK || mode == RUN_DENSE);
   if (item_space) { int rc = ensure_head_rows(h); if (rc) return rc; }
-  const int batch = item_space ? h->item_batch : kUserBatch;
+  const int batch = item_space ? h->batch_rows : kUserBatch;
   for (int b0 = 0; b0 < h->U; b0 += batch) {
     const int nb = std::min(batch, h->U - b0);
     if (item_space) {
       const int models = (need_ubm ? 1 : 0) | (need_ibm ? 2 : 0);
       {
         PhaseTimer t(h, MR_T_HEAD_ROWSUM);
-        MR_LAUNCH(h, launch_head_rowsum(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_g16, h->d_gq32, h->spitch,
-                                        h->S, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+        const int bi = b0 / batch;
+        const int* grp = h->d_grp_ptr + static_cast<long long>(bi) * (h->n_groups + 1);
+        const int sp0 = h->h_split_ptr[bi], n_split = h->h_split_ptr[bi + 1] - sp0;
+        if (need_ubm) {
+          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_u, h->spitch, h->stream));
+          MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, grp, h->n_groups, h->d_seg, h->d_hu_row, h->d_hu_song, h->d_hu_q, h->d_g16, h->d_gq32,
+                                          h->spitch, h->S, h->d_sint_u, h->spitch, h->stream));
+        }
+        if (need_ibm) {
+          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_i, h->spitch, h->stream));
+          MR_LAUNCH(h, launch_head_rowsum(2, h->head_words_i, grp, h->n_groups, h->d_seg, h->d_hu_row, h->d_hu_song, h->d_hu_q, h->d_g16, h->d_gq32,
+                                          h->spitch, h->S, h->d_sint_i, h->spitch, h->stream));
+        }
         if (h->n_ex > 0)
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
                                          h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
@@ -460,11 +547,14 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
     MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_col, b0, nb, need_ubm ? h->d_sint_u : nullptr,
                                       need_ibm ? h->d_sint_i : nullptr, h->spitch, h->stream));
     if (mode == RUN_DENSE) {
-      MR_LAUNCH(h, launch_dense_scores(model, need_ubm ? h->d_sint_u : h->d_sint_i, h->spitch, b0, nb, h->S, h->d_rsa, h->d_rsd,
-                                       h->d_dense, h->stream));
-      MR_CUDA(h, cudaMemcpyAsync(static_cast<double*>(host_out) + static_cast<long long>(b0) * h->S, h->d_dense,
-                                 static_cast<size_t>(nb) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      MR_CUDA(h, cudaStreamSynchronize(h->stream));
+      for (int c0 = 0; c0 < nb; c0 += kDenseChunk) {
+        const int cn = std::min(kDenseChunk, nb - c0);
+        MR_LAUNCH(h, launch_dense_scores(model, (need_ubm ? h->d_sint_u : h->d_sint_i) + static_cast<long long>(c0) * h->spitch, h->spitch, b0 + c0, cn,
+                                         h->S, h->d_rsa, h->d_rsd, h->d_dense, h->stream));
+        MR_CUDA(h, cudaMemcpyAsync(static_cast<double*>(host_out) + static_cast<long long>(b0 + c0) * h->S, h->d_dense,
+                                   static_cast<size_t>(cn) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MR_CUDA(h, cudaStreamSynchronize(h->stream));
+      }
     } else {
       if (model == MODEL_AGG || model == MODEL_STOCH)
         MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, b0, nb, h->S, h->d_sel, h->sel_pitch, h->stream));
@@ -637,11 +727,11 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_carry_seen), 4096 * sizeof(unsigned int)));
     memset(h->h_carry_seen, 0, 4096 * sizeof(unsigned int));
   }
-  if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch = std::max(128, atoi(e));
-  if ((rc = dev_alloc(h, &h->d_sint_u, static_cast<size_t>(h->item_batch) * h->spitch, h->allocs))) return rc;
-  if ((rc = dev_alloc(h, &h->d_sint_i, static_cast<size_t>(h->item_batch) * h->spitch, h->allocs))) return rc;
+  if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch_cap = std::max(128, atoi(e));
+  if (const char* e = getenv("MRSCORE_HEAD_WORDS_U")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_u = w; }
+  if (const char* e = getenv("MRSCORE_HEAD_WORDS_I")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_i = w; }
+  h->n_groups = h->num_sms * kHeadCtasPerSm;
   h->sel_pitch = (S + 63) / 64;
-  if ((rc = dev_alloc(h, &h->d_sel, static_cast<size_t>(h->item_batch) * h->sel_pitch, h->allocs))) return rc;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
     long long min_deg = std::max<long long>(2, S / 6000);   // below ~64 listeners expanding a song on the fly is cheaper than streaming its row
@@ -741,6 +831,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     if ((rc = slot_upload(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, tu_lptr.data(), tu_lptr.size()))) return rc;
     h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
+    if ((rc = plan_item_batches(h, hu_ptr))) return rc;
   }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_test = true;
@@ -922,7 +1013,7 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(h->item_batch) * h->S))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->S))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
   return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
@@ -1053,9 +1144,10 @@ int mr_reset_timing(mr_handle* h) {
 }
 int mr_get_info(mr_handle* h, int64_t* out, int n) {
   if (!h || !out) return MR_ERR_BAD_ARG;
-  const int64_t v[11] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
-                         h->n_head_entries, h->n_tail_entries, h->n_ex};
-  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+  const int64_t v[14] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
+                         h->n_head_entries, h->n_tail_entries, h->n_ex, h->batch_rows, h->n_groups,
+                         h->h_split_ptr.empty() ? 0 : h->h_split_ptr.back()};
+  for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
   return MR_OK;
 }
 int mr_prepare(mr_handle* h) {

@@ -316,10 +316,10 @@ class MusicRecommender:
         return dict(zip(_lib.TIMING_NAMES, list(t)))
 
     def info(self) -> dict:
-        v = (C.c_int64 * 11)()
-        self._lib.mr_get_info(self._h, v, 11)
+        v = (C.c_int64 * 14)()
+        self._lib.mr_get_info(self._h, v, 14)
         return dict(zip(["engine", "launches", "dense_bytes", "n_items", "num_sms", "device_bytes", "space", "n_head", "head_entries",
-                         "tail_entries", "head_exceptions"], list(v)))
+                         "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users"], list(v)))
 
     # ------------------------------------------------------------------ model file I/O (MR:489-512)
     def writeModelOnFile(self, model: Model, outputFileName: str = "") -> None:

@@ -144,6 +144,34 @@ def test_long_rows_take_the_sampled_topk_path(oracle_lib):
         check_dataset(ds, oracle_lib, cfg, blends=True)
 
 
+def test_item_space_balanced_groups_and_batches(oracle_lib, monkeypatch):
+    """More test users than head_rowsum work groups (148 SMs x 8): groups hold several segments, heavy users are split over groups
+    and accumulate atomically, and a capped batch size makes the shard span several batches — all still the oracle's bits.
+    Every row-load width of the head pass is covered."""
+    ds = synth(T=2500, U=2700, S=3100, seed=12)
+    want = {"ubm": oracle_lib.canon_scores(ds, oracle_lib.UBM), "ibm": oracle_lib.canon_scores(ds, oracle_lib.IBM)}
+    for cap, words in (("", "4"), ("1000", "2"), ("128", "1")):
+        if cap:
+            monkeypatch.setenv("MRSCORE_ITEM_BATCH", cap)
+        monkeypatch.setenv("MRSCORE_HEAD_WORDS_U", words)
+        monkeypatch.setenv("MRSCORE_HEAD_WORDS_I", words)
+        with MusicRecommender(ds, engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM) as mr:
+            info = mr.info()
+            assert info["batch_rows"] == (ds.U if not cap else max(128, -(-ds.U // -(-ds.U // int(cap)))))
+            assert info["split_users"] > 0
+            assert_bits_equal(mr.getUserBasedModel().scores, want["ubm"])
+            assert_bits_equal(mr.getItemBasedModel().scores, want["ibm"])
+            for key, kind in KINDS.items():
+                song, score, ln = mr.getTopK(kind, k=100)
+                ws, wv, wl = oracle_lib.topk(want[key], 100)
+                np.testing.assert_array_equal(song, ws)
+                assert_bits_equal(score, wv)
+            song, score, ln = mr.getTopK(_lib.MR_LC, k=100, param=0.25)
+            ws, wv, wl = oracle_lib.topk(oracle_lib.blend_dense(oracle_lib.LC, 0.25, want["ubm"], want["ibm"], 0), 100)
+            np.testing.assert_array_equal(song, ws)
+            assert_bits_equal(score, wv)
+
+
 def test_config_c1(engine, oracle_lib):
     ds = synth_config("c1")
     info = check_dataset(ds, oracle_lib, engine)
