@@ -14,6 +14,7 @@
 #include "mr_kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace mr {
 
@@ -118,50 +119,55 @@ template <> __device__ __forceinline__ RowWords<4> ld_row_words<4>(const void* p
   const uint4 v = __ldg(static_cast<const uint4*>(p)); RowWords<4> r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w; return r;
 }
 
-// kIbm = false: UBM pass over Gq32 (W songs per thread).  kIbm = true: IBM pass over G16 (2 W songs per thread, weight qd[j] per row,
-// the entry s == j excluded: `s2 != song`, MusicRecommender.scala:252).
+// kIbm = false: UBM pass over Gq32 (W songs per thread).  kIbm = true: IBM pass over G16 (2 W songs per thread, weight qd[j] per row).
+// The reference's `s2 != song` (MusicRecommender.scala:252) needs no test here: s == j happens only at s in I_u, a listened pair that
+// getModel never emits (MR:109) — mask_listened_kernel overwrites those entries before anything reads them.
+// A group's segments and entries (head row index, weight) are contiguous in the group-ordered arrays the host built; the CTA stages
+// them in shared memory with one coalesced round of loads, so the inner loop's only global accesses are the row loads themselves
+// (no dependent index -> row chain per round).
 template <bool kIbm, int W>
-__global__ void __launch_bounds__(256, kIbm ? kHeadCtasPerSm / 2 : kHeadCtasPerSm)
-head_rowsum_kernel(const int* __restrict__ grp_ptr, const int4* __restrict__ seg, const int* __restrict__ hu_row,
-                   const int* __restrict__ hu_song, const uint32_t* __restrict__ hu_q, const uint16_t* __restrict__ g16,
+__global__ void __launch_bounds__(256, kHeadCtasPerSm)
+head_rowsum_kernel(const int4* __restrict__ grp_hdr, const int4* __restrict__ seg, const int* __restrict__ ge_row,
+                   const uint32_t* __restrict__ ge_q, int seg_cap, int ent_cap, const uint16_t* __restrict__ g16,
                    const uint32_t* __restrict__ gq32, long long pitch, int n_songs, long long* __restrict__ sint, long long spitch) {
   constexpr int kVec = kIbm ? 2 * W : W;
-  constexpr int kRows = W == 4 ? 4 : 8;                       // rows in flight per thread
+  constexpr int kRows = kIbm ? (W == 1 ? 4 : 2) : (W == 4 ? 4 : 8);   // rows in flight per thread
+  extern __shared__ int4 s_dyn[];
+  int4* s_seg = s_dyn;                                                // [seg_cap]
+  int* s_row = reinterpret_cast<int*>(s_dyn + seg_cap);               // [ent_cap]
+  uint32_t* s_q = reinterpret_cast<uint32_t*>(s_row + ent_cap);       // [ent_cap] (IBM only)
+  const int4 hd = __ldg(grp_hdr + blockIdx.x);                        // x: first segment, y: segments, z: first entry, w: entries
+  for (int i = threadIdx.x; i < hd.y; i += blockDim.x) s_seg[i] = __ldg(seg + hd.x + i);
+  for (int i = threadIdx.x; i < hd.w; i += blockDim.x) {
+    s_row[i] = __ldg(ge_row + hd.z + i);
+    if (kIbm) s_q[i] = __ldg(ge_q + hd.z + i);
+  }
+  __syncthreads();
   const int s = kVec * (blockIdx.y * blockDim.x + threadIdx.x);
   if (s >= n_songs) return;
   const char* base = kIbm ? reinterpret_cast<const char*>(g16 + s) : reinterpret_cast<const char*>(gq32 + s);
   const long long row_bytes = pitch * (kIbm ? 2 : 4);
-  for (int gi = __ldg(grp_ptr + blockIdx.x), ge = __ldg(grp_ptr + blockIdx.x + 1); gi < ge; ++gi) {
-    const int4 sg = __ldg(seg + gi);                          // x: Sint row, y..z: head entries, w: accumulate into a pre-zeroed row
+  for (int gi = 0; gi < hd.y; ++gi) {
+    const int4 sg = s_seg[gi];                                        // x: Sint row, y..z: staged entries, w: accumulate into a pre-zeroed row
     unsigned long long acc[kVec];
 #pragma unroll
     for (int t = 0; t < kVec; ++t) acc[t] = 0;
-    auto add_row = [&](const RowWords<W>& c, uint32_t q, int j) {
-      if (!kIbm) {
+    auto add_row = [&](const RowWords<W>& c, uint32_t q) {
 #pragma unroll
-        for (int t = 0; t < W; ++t) acc[t] += c.w[t];
-      } else {
-        const int d = j - s;
-#pragma unroll
-        for (int t = 0; t < W; ++t) {
-          if (d != 2 * t) acc[2 * t] += static_cast<unsigned long long>(c.w[t] & 0xffffu) * q;
-          if (d != 2 * t + 1) acc[2 * t + 1] += static_cast<unsigned long long>(c.w[t] >> 16) * q;
-        }
+      for (int t = 0; t < W; ++t) {
+        if (!kIbm) acc[t] += c.w[t];
+        else { acc[2 * t] += static_cast<unsigned long long>(c.w[t] & 0xffffu) * q; acc[2 * t + 1] += static_cast<unsigned long long>(c.w[t] >> 16) * q; }
       }
     };
     int i = sg.y;
     for (; i + kRows <= sg.z; i += kRows) {
-      RowWords<W> c[kRows]; uint32_t q[kRows]; int js[kRows];
+      RowWords<W> c[kRows];
 #pragma unroll
-      for (int t = 0; t < kRows; ++t) {
-        c[t] = ld_row_words<W>(base + static_cast<long long>(__ldg(hu_row + i + t)) * row_bytes);
-        if (kIbm) { q[t] = __ldg(hu_q + i + t); js[t] = __ldg(hu_song + i + t); } else { q[t] = 0; js[t] = 0; }
-      }
+      for (int t = 0; t < kRows; ++t) c[t] = ld_row_words<W>(base + static_cast<long long>(s_row[i + t]) * row_bytes);
 #pragma unroll
-      for (int t = 0; t < kRows; ++t) add_row(c[t], q[t], js[t]);
+      for (int t = 0; t < kRows; ++t) add_row(c[t], kIbm ? s_q[i + t] : 0u);
     }
-    for (; i < sg.z; ++i)
-      add_row(ld_row_words<W>(base + static_cast<long long>(__ldg(hu_row + i)) * row_bytes), kIbm ? __ldg(hu_q + i) : 0u, kIbm ? __ldg(hu_song + i) : 0);
+    for (; i < sg.z; ++i) add_row(ld_row_words<W>(base + static_cast<long long>(s_row[i]) * row_bytes), kIbm ? s_q[i] : 0u);
     unsigned long long* o = reinterpret_cast<unsigned long long*>(sint) + static_cast<long long>(sg.x) * spitch + s;
     if (sg.w) {
 #pragma unroll
@@ -175,15 +181,16 @@ head_rowsum_kernel(const int* __restrict__ grp_ptr, const int4* __restrict__ seg
   }
 }
 
-int head_rowsum_tile_songs(int model, int words) { return 256 * (model == 2 ? 2 * words : words); }
-
-int launch_head_rowsum(int model, int words, const int* grp_ptr, int n_groups, const int4* seg, const int* hu_row, const int* hu_song,
-                       const uint32_t* hu_q, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint,
-                       long long spitch, cudaStream_t st) {
+int launch_head_rowsum(int model, int words, int threads, const int4* grp_hdr, int n_groups, const int4* seg, const int* ge_row,
+                       const uint32_t* ge_q, int seg_cap, int ent_cap, const uint16_t* g16, const uint32_t* gq32, long long pitch,
+                       int n_songs, long long* sint, long long spitch, cudaStream_t st) {
   if (n_groups <= 0 || n_songs <= 0) return 0;
-  const int tile = head_rowsum_tile_songs(model, words);
+  if (threads < 32 || threads > 256 || threads % 32) return -2;
+  const int tile = threads * (model == 2 ? 2 * words : words);   // songs per CTA
   const dim3 grid(n_groups, (n_songs + tile - 1) / tile);
-#define MR_HR(IBM, W) head_rowsum_kernel<IBM, W><<<grid, 256, 0, st>>>(grp_ptr, seg, hu_row, hu_song, hu_q, g16, gq32, pitch, n_songs, sint, spitch)
+  const size_t smem = static_cast<size_t>(seg_cap) * sizeof(int4) + static_cast<size_t>(ent_cap) * 8;
+  if (smem > 48 * 1024) return -3;
+#define MR_HR(IBM, W) head_rowsum_kernel<IBM, W><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch)
   if (model == 1) { if (words == 4) MR_HR(false, 4); else if (words == 2) MR_HR(false, 2); else if (words == 1) MR_HR(false, 1); else return -2; }
   else if (model == 2) { if (words == 4) MR_HR(true, 4); else if (words == 2) MR_HR(true, 2); else if (words == 1) MR_HR(true, 1); else return -2; }
   else return -2;

@@ -6,7 +6,7 @@
 namespace mr {
 
 constexpr int kUserBatch = 128;   // test users per batch of the user-space engine = UMMA M
-constexpr int kHeadCtasPerSm = 8;  // head_rowsum groups per SM: one wave of CTAs covers one song tile for the whole batch
+constexpr int kHeadCtasPerSm = 8;  // head_rowsum: resident 256-thread CTAs per SM the UBM pass is compiled for (32 registers per thread)
 constexpr int kDenseChunk = 1184;  // rows per device->host chunk of mr_score_dense
 constexpr int kTailSubBatch = 296; // tail scatter runs per 296 users so its atomics stay within a ~1.8 GB slice of the Sint panels
 // Count panels K1 hands to K2, train-user-major so that one gathered row serves the whole 128-user batch in one coalesced read:
@@ -67,11 +67,11 @@ int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int
                              long long pitch, int num_sms, cudaStream_t st);
 int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r0, int n_rows, long long pitch, uint16_t* g16,
                           uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
-// model: 1 = UBM pass over Gq32, 2 = IBM pass over G16; words = 32-bit words per row load (1, 2 or 4); groups / segments: see k4_itemspace.cu
-int launch_head_rowsum(int model, int words, const int* grp_ptr, int n_groups, const int4* seg, const int* hu_row, const int* hu_song,
-                       const uint32_t* hu_q, const uint16_t* g16, const uint32_t* gq32, long long pitch, int n_songs, long long* sint,
-                       long long spitch, cudaStream_t st);
-int head_rowsum_tile_songs(int model, int words);
+// model: 1 = UBM pass over Gq32, 2 = IBM pass over G16; words = 32-bit words per row load (1, 2 or 4); threads per CTA (a CTA covers
+// threads * songs-per-thread songs); groups / segments: see k4_itemspace.cu
+int launch_head_rowsum(int model, int words, int threads, const int4* grp_hdr, int n_groups, const int4* seg, const int* ge_row,
+                       const uint32_t* ge_q, int seg_cap, int ent_cap, const uint16_t* g16, const uint32_t* gq32, long long pitch,
+                       int n_songs, long long* sint, long long spitch, cudaStream_t st);
 int launch_zero_rows(const int* rows, int n_rows, long long* sint, long long spitch, cudaStream_t st);
 int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, const int* hu_song, const uint32_t* hu_q, int u0, int n_users,
                       const long long* ex_ptr, const int* ex_song, const uint32_t* ex_g, const unsigned long long* ex_gq,

@@ -48,8 +48,9 @@ struct mr_handle {
   int space_flag = MR_SPACE_AUTO; int space = MR_SPACE_USER; int n_head = 0; bool head_ready = false;
   int item_batch_cap = 0;              // MRSCORE_ITEM_BATCH: upper bound on test users per item-space batch (0 = as many as fit in HBM)
   int batch_rows = kUserBatch;         // test users per batch of the current shard = rows of the Sint panels
-  int head_words_u = 4, head_words_i = 4, n_groups = 0;   // head_rowsum: 32-bit words per row load (UBM / IBM pass), groups per batch
-  int4* d_seg = nullptr; int* d_grp_ptr = nullptr; int* d_split_rows = nullptr; std::vector<int> h_split_ptr;   // balanced work groups per batch
+  int head_words_u = 4, head_words_i = 4, head_threads = 128, n_groups = 0;   // head_rowsum: 32-bit words per row load (UBM / IBM pass), groups per batch
+  int4 *d_seg = nullptr, *d_grp_hdr = nullptr; int *d_ge_row = nullptr, *d_split_rows = nullptr; uint32_t* d_ge_q = nullptr; int seg_cap = 1, ent_cap = 1;
+  std::vector<int> h_split_ptr;   // balanced work groups per batch
   std::vector<int> head_index;         // song -> head row or -1
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
   long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
@@ -59,7 +60,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_SEG, SL_GRP_PTR, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -387,7 +388,7 @@ int ensure_head_rows(mr_handle* h) {
 // panels (two models, 8 bytes per (user, song)) fit in HBM next to the head rows — a large batch shares the row tiles of popular
 // songs among more users (head_rowsum_kernel) — split evenly, plus per batch the balanced work groups of head_rowsum_kernel:
 // segments (Sint row, head-entry range) packed longest-first into n_groups bins of equal total length.
-int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
+int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const std::vector<int>& hu_row, const std::vector<uint32_t>& hu_q) {
   int rc;
   const int U = h->U;
   h->batch_rows = kUserBatch;
@@ -412,8 +413,10 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
 
   const int G = h->n_groups, B = h->batch_rows;
   const int n_batches = (U + B - 1) / B;
-  std::vector<int4> seg; std::vector<int> grp_ptr; std::vector<int> split_rows;
+  std::vector<int4> seg, grp_hdr; std::vector<int> ge_row, split_rows; std::vector<uint32_t> ge_q;
+  ge_row.reserve(hu_row.size()); ge_q.reserve(hu_q.size());
   h->h_split_ptr.assign(1, 0);
+  h->seg_cap = 1; h->ent_cap = 1;
   struct Item { int row, e0, e1, acc; };
   std::vector<Item> items; std::vector<std::vector<int>> bins(G);
   for (int bi = 0; bi < n_batches; ++bi) {
@@ -441,14 +444,25 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
       bins[top.second].push_back(static_cast<int>(i));
       heap.push({top.first + (items[i].e1 - items[i].e0) + kRowCost, top.second});
     }
-    for (int g = 0; g < G; ++g) {
-      grp_ptr.push_back(static_cast<int>(seg.size()));
-      for (int i : bins[g]) seg.push_back(make_int4(items[i].row, items[i].e0, items[i].e1, items[i].acc));
+    for (int g = 0; g < G; ++g) {   // the group's segments and entries, contiguous: the CTA stages them in shared memory
+      const int seg0 = static_cast<int>(seg.size()), ent0 = static_cast<int>(ge_row.size());
+      for (int i : bins[g]) {
+        const int local = static_cast<int>(ge_row.size()) - ent0, n = items[i].e1 - items[i].e0;
+        seg.push_back(make_int4(items[i].row, local, local + n, items[i].acc));
+        ge_row.insert(ge_row.end(), hu_row.begin() + items[i].e0, hu_row.begin() + items[i].e1);
+        ge_q.insert(ge_q.end(), hu_q.begin() + items[i].e0, hu_q.begin() + items[i].e1);
+      }
+      const int n_seg = static_cast<int>(seg.size()) - seg0, n_ent = static_cast<int>(ge_row.size()) - ent0;
+      grp_hdr.push_back(make_int4(seg0, n_seg, ent0, n_ent));
+      h->seg_cap = std::max(h->seg_cap, n_seg); h->ent_cap = std::max(h->ent_cap, n_ent);
     }
-    grp_ptr.push_back(static_cast<int>(seg.size()));
   }
+  if (static_cast<size_t>(h->seg_cap) * 16 + static_cast<size_t>(h->ent_cap) * 8 > 48 * 1024)
+    return fail(h, MR_ERR_BAD_ARG, "head_rowsum work group too large for shared-memory staging (%d segments, %d entries)", h->seg_cap, h->ent_cap);
   if ((rc = slot_upload(h, mr_handle::SL_SEG, &h->d_seg, seg.data(), seg.size()))) return rc;
-  if ((rc = slot_upload(h, mr_handle::SL_GRP_PTR, &h->d_grp_ptr, grp_ptr.data(), grp_ptr.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_GRP_HDR, &h->d_grp_hdr, grp_hdr.data(), grp_hdr.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_GE_ROW, &h->d_ge_row, ge_row.data(), ge_row.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_GE_Q, &h->d_ge_q, ge_q.data(), ge_q.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_SPLIT_ROWS, &h->d_split_rows, split_rows.data(), split_rows.size()))) return rc;
   MR_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging vectors above are pageable and go out of scope
   return MR_OK;
@@ -469,16 +483,16 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       {
         PhaseTimer t(h, MR_T_HEAD_ROWSUM);
         const int bi = b0 / batch;
-        const int* grp = h->d_grp_ptr + static_cast<long long>(bi) * (h->n_groups + 1);
+        const int4* grp = h->d_grp_hdr + static_cast<long long>(bi) * h->n_groups;
         const int sp0 = h->h_split_ptr[bi], n_split = h->h_split_ptr[bi + 1] - sp0;
         if (need_ubm) {
           if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_u, h->spitch, h->stream));
-          MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, grp, h->n_groups, h->d_seg, h->d_hu_row, h->d_hu_song, h->d_hu_q, h->d_g16, h->d_gq32,
+          MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
                                           h->spitch, h->S, h->d_sint_u, h->spitch, h->stream));
         }
         if (need_ibm) {
           if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_i, h->spitch, h->stream));
-          MR_LAUNCH(h, launch_head_rowsum(2, h->head_words_i, grp, h->n_groups, h->d_seg, h->d_hu_row, h->d_hu_song, h->d_hu_q, h->d_g16, h->d_gq32,
+          MR_LAUNCH(h, launch_head_rowsum(2, h->head_words_i, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
                                           h->spitch, h->S, h->d_sint_i, h->spitch, h->stream));
         }
         if (h->n_ex > 0)
@@ -730,7 +744,8 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch_cap = std::max(128, atoi(e));
   if (const char* e = getenv("MRSCORE_HEAD_WORDS_U")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_u = w; }
   if (const char* e = getenv("MRSCORE_HEAD_WORDS_I")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_i = w; }
-  h->n_groups = h->num_sms * kHeadCtasPerSm;
+  if (const char* e = getenv("MRSCORE_HEAD_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) h->head_threads = t; }
+  h->n_groups = h->num_sms * std::min(32, kHeadCtasPerSm * 256 / h->head_threads);   // one wave of resident CTAs = one song tile for the whole batch
   h->sel_pitch = (S + 63) / 64;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
@@ -831,7 +846,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     if ((rc = slot_upload(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, tu_lptr.data(), tu_lptr.size()))) return rc;
     h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
-    if ((rc = plan_item_batches(h, hu_ptr))) return rc;
+    if ((rc = plan_item_batches(h, hu_ptr, hu_row, hu_q))) return rc;
   }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_test = true;
