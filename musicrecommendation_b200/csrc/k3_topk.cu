@@ -129,15 +129,20 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 // ---------------------------------------------------------------- top-k select
 // One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
 // the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
-// The monotone map bin(score) = floor(score * 2047 / max) is only ever a PRE-FILTER; exactness comes from the final sort.
-//   long rows (S > 65536):  A1 max and A2 2048-bin histogram over every 8th 4096-song chunk (1/8 of the row each) predict a cut
-//                           bin with ~1.5 k keys above it; ONE full pass collects the keys at or above the cut and counts the valid
-//                           ones; accepted when min(k, valid) <= collected <= 2048, i.e. 1.25 passes over the row in total
-//   otherwise / on reject:  exact path — full histogram, the bin holding the k-th best key, collect pass
+// Every bin map below is monotone in the key and only ever a PRE-FILTER; exactness comes from the final sort of the collected keys.
+//   long rows (S > 65536), fast path — 1.25 passes over the row:
+//     A1  maximum over every 8th chunk of the row (1/8 of it)
+//     A2  2048-bin logarithmic histogram (64 bins per binade below the maximum) over the same chunks; the bin above which about
+//         (k + k/2) / 8 sampled keys lie gives the cut
+//     B   ONE full pass collects the keys at or above the cut; accepted when min(k, valid) <= collected <= 2048
+//     For the pure UBM model the score (double)Sint * rsu is strictly monotone in the integer numerator, so A1/A2/B work on the
+//     integers (one 64-bit compare per song in B) and only the collected keys are converted to fp64.  The other models evaluate the
+//     fp64 score per song (blends included) and compare its bit pattern.
+//     valid = S - |I_u| needs no counting: the listened pairs are exactly the sentinel entries (getModel's filter, MR:109).
+//   otherwise / on reject:  exact path — full linear histogram, the bin holding the k-th best key, collect pass
 //   degenerate rows (thousands of exact ties such as all-zero rows, or a bin more crowded than the candidate buffer): exact
 //                           most-significant-digit radix select (8-bit digits of the 96-bit key) inside the chosen bin
 // The collected keys (<= 2048) are bitonic-sorted exactly in shared memory: key descending, song ascending.
-// Every pass streams the row with 4 songs per thread (16-byte loads, 4 independent keys in flight per thread).
 constexpr int kTopkThreads = 512;
 constexpr int kTopkCap = 2048;    // candidate buffer (>= 2 * k); bitonic-sorted in shared memory
 constexpr int kTopkBins = 2048;
@@ -216,8 +221,160 @@ __device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool ok, int l
   if ((pending >> lane) & 1u) atomicAdd(&hist[bin], 1);
 }
 
+// ---- fast path helpers.  "Proxy" p of a song: the integer numerator (pure UBM) or the fp64 score bits (every other model); the
+// logarithmic bin of a proxy keeps its exponent and 6 mantissa bits: lb(p) = bits(float_rz(p)) >> 17 resp. bits(double) >> 46.
+__device__ __forceinline__ uint32_t logbits_int(long long a) { return a > 0 ? __float_as_uint(__ll2float_rz(a)) >> 17 : 0u; }
+__device__ __forceinline__ uint32_t logbits_key(unsigned long long kb) { return static_cast<uint32_t>(kb >> 46); }
+
+// Visit the row 4 songs per thread per step, two steps in flight: f(song of the first of 4, a[4], b[4], rsd[4], select word) with a = -1 /
+// b = -1 where the model does not use that panel; entries past the end of the row are reported as listened (-1).
+template <bool kInt, class F>
+__device__ __forceinline__ void visit_row(const KeyCtx& c, int n_songs, int chunk_stride, F&& f) {
+  constexpr int kSteps = kInt ? 2 : 1;                          // steps in flight (the fp64 models already load three arrays per step)
+  const int step = 4 * kTopkThreads * chunk_stride;
+  for (int base0 = 0; base0 < n_songs; base0 += kSteps * step) {   // the same trip count for every thread: f may use warp collectives
+    const int base = base0 + 4 * static_cast<int>(threadIdx.x);
+    long long a[kSteps][4], b[kSteps][4]; double rd[kSteps][4]; uint64_t selw[kSteps];
+#pragma unroll
+    for (int h = 0; h < kSteps; ++h) {
+      const int s = base + h * step;
+      selw[h] = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { a[h][t] = -1; b[h][t] = -1; rd[h][t] = 0.0; }
+      if (s < n_songs) {   // rows are padded to a multiple of 32 songs, so the 4-wide loads stay inside the row
+        if (kInt || c.model != MODEL_IBM) {
+          const longlong2 x = __ldcs(reinterpret_cast<const longlong2*>(c.su + s)), y = __ldcs(reinterpret_cast<const longlong2*>(c.su + s + 2));
+          a[h][0] = x.x; a[h][1] = x.y; a[h][2] = y.x; a[h][3] = y.y;
+        }
+        if (!kInt && c.model != MODEL_UBM) {
+          const longlong2 x = __ldcs(reinterpret_cast<const longlong2*>(c.si + s)), y = __ldcs(reinterpret_cast<const longlong2*>(c.si + s + 2));
+          b[h][0] = x.x; b[h][1] = x.y; b[h][2] = y.x; b[h][3] = y.y;
+          if (s + 4 <= n_songs) {
+            const double2 r0 = __ldg(reinterpret_cast<const double2*>(c.rsd + s)), r1 = __ldg(reinterpret_cast<const double2*>(c.rsd + s + 2));
+            rd[h][0] = r0.x; rd[h][1] = r0.y; rd[h][2] = r1.x; rd[h][3] = r1.y;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s + t < n_songs) rd[h][t] = __ldg(c.rsd + s + t);
+          }
+        }
+        if (!kInt && c.model >= MODEL_AGG) selw[h] = c.sel[s >> 6] >> (s & 63);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (s + t >= n_songs) { a[h][t] = -1; b[h][t] = -1; }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kSteps; ++h) f(base + h * step, a[h], b[h], rd[h], selw[h]);
+  }
+}
+
+// proxy of one song (0 = not a candidate: listened, past the end, or a zero score — zero scores are only ever needed when fewer than k
+// positive ones exist, which the acceptance test catches)
+template <bool kInt>
+__device__ __forceinline__ unsigned long long proxy_of(const KeyCtx& c, long long a, long long b, double rd, bool pick) {
+  if (kInt) return a > 0 ? static_cast<unsigned long long>(a) : 0ULL;
+  bool ok = true;
+  if (c.model != MODEL_IBM) ok = ok && a >= 0;
+  if (c.model != MODEL_UBM) ok = ok && b >= 0;
+  return ok ? static_cast<unsigned long long>(__double_as_longlong(blend_score(c.model, a, b, c.rsu, rd, c.alpha, c.oma, pick))) : 0ULL;
+}
+
+// Fast path for long rows; returns true when the candidate buffer holds a superset of the top `need` keys (s_count of them).
+// *scale_out = the linear-bin scale of the exact path (from the sampled maximum), so a rejected row continues there.
+template <bool kInt>
+__device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int stride, int k, int need, unsigned long long* s_key, int* s_song,
+                                               int* s_hist, unsigned long long* s_max, int* s_count, int* s_ctl, double* max_score_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- A1: sampled maximum of the proxy
+  unsigned long long mx = 0;
+  visit_row<kInt>(c, n_songs, stride, [&](int, const long long* a, const long long* b, const double* rd, uint64_t selw) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const unsigned long long p = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); mx = p > mx ? p : mx; }
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
+  if (lane == 0) s_max[warp] = mx;
+  for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+  if (tid == 0) *s_count = 0;
+  __syncthreads();
+  mx = 0;
+  for (int i = 0; i < kTopkThreads / 32; ++i) mx = s_max[i] > mx ? s_max[i] : mx;
+  *max_score_out = kInt ? __dmul_rn(__ll2double_rn(static_cast<long long>(mx)), c.rsu) : __longlong_as_double(static_cast<long long>(mx));
+  const uint32_t top = kInt ? logbits_int(static_cast<long long>(mx)) : logbits_key(mx);
+  auto bin_of = [&](unsigned long long p) -> uint32_t {     // 0 for p == 0; monotone in p; the sampled maximum lands in the top bin
+    if (p == 0) return 0u;
+    const uint32_t lb = kInt ? logbits_int(static_cast<long long>(p)) : logbits_key(p);
+    const int d = static_cast<int>(kTopkBins - 1) - (static_cast<int>(top) - static_cast<int>(lb));
+    return static_cast<uint32_t>(d < 1 ? 1 : (d > kTopkBins - 1 ? kTopkBins - 1 : d));
+  };
+  // ---- A2: histogram over the same chunks
+  visit_row<kInt>(c, n_songs, stride, [&](int, const long long* a, const long long* b, const double* rd, uint64_t selw) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned long long p = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL);
+      hist_add(s_hist, bin_of(p), p != 0, lane);
+    }
+  });
+  __syncthreads();
+  // ---- the cut: highest bin with at least `want` sampled keys in it or above (warp 0); bins >= 2 only, so the threshold is a real proxy value
+  if (warp == 0) {
+    const int want = (k + k / 2 + 64 + stride - 1) / stride;
+    int part = 0;
+    for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
+    int above_lane = 0;
+    for (int l = 0; l < 32; ++l) { const int pp = __shfl_sync(0xffffffffu, part, l); if (l > lane) above_lane += pp; }
+    if (lane == 0) s_ctl[0] = 0;
+    __syncwarp();
+    if (above_lane < want && above_lane + part >= want) {
+      int cum = above_lane, chosen = lane * (kTopkBins / 32);
+      for (int i = kTopkBins / 32 - 1; i >= 0; --i) {
+        const int bin = lane * (kTopkBins / 32) + i;
+        if (cum + s_hist[bin] >= want) { chosen = bin; break; }
+        cum += s_hist[bin];
+      }
+      s_ctl[0] = chosen;
+    }
+  }
+  __syncthreads();
+  const int cut = s_ctl[0];
+  if (cut < 2) return false;                     // too few positive keys in the sample: let the exact path decide
+  // smallest proxy whose bin is >= cut: log bits >= top - (2047 - cut)
+  const long long lb_cut = static_cast<long long>(top) - (kTopkBins - 1 - cut);
+  if (lb_cut <= 0) return false;
+  unsigned long long thr;
+  if (kInt) thr = static_cast<unsigned long long>(__float2ll_ru(__uint_as_float(static_cast<uint32_t>(lb_cut) << 17)));
+  else thr = static_cast<unsigned long long>(lb_cut) << 46;
+  // ---- B: one full pass, collect every song whose proxy is at or above the threshold
+  visit_row<kInt>(c, n_songs, 1, [&](int s, const long long* a, const long long* b, const double* rd, uint64_t selw) {
+    unsigned long long p[4];
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { p[t] = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); any = any || p[t] >= thr; }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const bool ok = p[t] >= thr;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(s_count, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (ok) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < kTopkCap) {
+              s_key[pos] = kInt ? static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(a[t]), c.rsu))) : p[t];
+              s_song[pos] = s + t;
+            }
+          }
+        }
+      }
+    }
+  });
+  __syncthreads();
+  return *s_count >= need && *s_count <= kTopkCap;
+}
+
 __global__ void __launch_bounds__(kTopkThreads, 2)
-topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long long* __restrict__ sint_i, long long spitch,
+topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long long* __restrict__ sint_u, const long long* __restrict__ sint_i, long long spitch,
             const uint64_t* __restrict__ sel, long long sel_pitch_words, int u0, int n_songs, const double* __restrict__ rsa,
             const double* __restrict__ rsd, int k, int* __restrict__ out_song, double* __restrict__ out_score,
             int* __restrict__ out_len) {
@@ -225,7 +382,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   __shared__ int s_song[kTopkCap];
   __shared__ int s_hist[kTopkBins];
   __shared__ unsigned long long s_max[kTopkThreads / 32];
-  __shared__ int s_count, s_valid;
+  __shared__ int s_count;
   __shared__ int s_ctl[4];     // 0: chosen bin / digit, 1: keys strictly above it, 2: keys in it, 3: need
 
   const int b = blockIdx.x;
@@ -240,20 +397,31 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
 
-  // ---- pass A1: (sampled) row maximum.  Any scale keeps the bin map monotone — scores above a too-small estimate simply
-  // share the top bin — so long rows look at every 8th 4096-song chunk only.
   const int stride = n_songs > 65536 ? 8 : 1;
-  unsigned long long mx = 0;
-  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; }, stride);
+  const int n_valid = n_songs - static_cast<int>(te_ptr[u + 1] - te_ptr[u]);   // scored pairs of this user (MR:109)
+  int need = 0;
+  bool collected = false;
+  double max_score = 0.0;
+  if (stride > 1) {
+    need = min(k, n_valid);
+    if (c.model == MODEL_UBM && bp.ubm_int_ok && c.rsu > 0.0)
+      collected = topk_fast_path<true>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score);
+    else
+      collected = topk_fast_path<false>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score);
+    __syncthreads();
+  } else {
+    // ---- short rows: exact maximum
+    unsigned long long mx = 0;
+    scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { if (ok && kb > mx) mx = kb; });
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
-  if (lane == 0) s_max[warp] = mx;
-  for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
-  if (tid == 0) { s_count = 0; s_valid = 0; }
-  __syncthreads();
-  mx = 0;
-  for (int i = 0; i < kTopkThreads / 32; ++i) mx = s_max[i] > mx ? s_max[i] : mx;
-  const double max_score = __longlong_as_double(static_cast<long long>(mx));
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    mx = 0;
+    for (int i = 0; i < kTopkThreads / 32; ++i) mx = s_max[i] > mx ? s_max[i] : mx;
+    max_score = __longlong_as_double(static_cast<long long>(mx));
+  }
+  // linear bin map of the exact path; any scale keeps it monotone (scores above a sampled maximum share the top bin)
   const double scale = max_score > 0.0 ? __ddiv_rn(static_cast<double>(kTopkBins - 1), max_score) : 0.0;
   auto bin_of = [&](unsigned long long kb) -> uint32_t {
     const int d = __double2int_rz(__dmul_rn(__longlong_as_double(static_cast<long long>(kb)), scale));
@@ -283,68 +451,14 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
       }
     }
   };
-
-  // ---- pass A2: histogram of the monotone bin map over the same (sampled) chunks
-  scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); }, stride);
-  __syncthreads();
-
-  int need = 0;
-  bool collected = false;
   uint32_t cbin = 0; unsigned long long phi = 0; uint32_t plo = 0; int nd = 0;
-  if (stride > 1) {
-    // ---- fast path for long rows: the sample predicts a cut bin above which about 1.5 k keys lie; ONE full pass collects every
-    // key at or above it and counts the valid keys.  It is exact whenever at least min(k, valid) and at most kTopkCap keys were
-    // collected (the cut is only a pre-filter); otherwise the exact three-pass path below runs.
-    find_bin((k + k / 2 + 64 + stride - 1) / stride, false);
+  if (!collected) {
+    // ---- exact histogram over the whole row
+    for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+    if (tid == 0) s_count = 0;
     __syncthreads();
-    const uint32_t cut = static_cast<uint32_t>(s_ctl[0]);
+    scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); });
     __syncthreads();
-    // smallest key whose bin is >= cut (positive doubles order like their bit patterns): start at cut / scale and walk a few ulps
-    unsigned long long t_kb = 0;
-    if (cut > 0 && scale > 0.0) {
-      t_kb = static_cast<unsigned long long>(__double_as_longlong(__ddiv_rn(static_cast<double>(cut), scale)));
-      for (int i = 0; i < 64 && t_kb > 0 && bin_of(t_kb - 1) >= cut; ++i) --t_kb;
-      for (int i = 0; i < 64 && bin_of(t_kb) < cut; ++i) ++t_kb;
-    }
-    // pure UBM: the same threshold on the integer numerator (score = (double)Sint * rsu is monotone in Sint), so that the pass
-    // compares integers and only converts the handful of keys it keeps
-    long long ubm_min = 0;
-    if (c.model == MODEL_UBM && c.rsu > 0.0 && t_kb > 0) {
-      auto key_of = [&](long long v) { return static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(v), c.rsu))); };
-      ubm_min = __double2ll_rd(__ddiv_rn(__longlong_as_double(static_cast<long long>(t_kb)), c.rsu));
-      for (int i = 0; i < 64 && ubm_min > 0 && key_of(ubm_min - 1) >= t_kb; ++i) --ubm_min;
-      for (int i = 0; i < 64 && key_of(ubm_min) < t_kb; ++i) ++ubm_min;
-      if (key_of(ubm_min) < t_kb || (ubm_min > 0 && key_of(ubm_min - 1) >= t_kb)) ubm_min = 0;   // not the exact boundary: no pre-filter
-    }
-    int my_valid = 0;
-    scan_row(c, n_songs, [&](int s, unsigned long long kb, bool ok) {
-      my_valid += ok;
-      ok = ok && kb >= t_kb && (t_kb > 0 || cut == 0);
-      const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (ok) {
-          const int pos = base + __popc(m & ((1u << lane) - 1));
-          if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s; }
-        }
-      }
-    }, 1, ubm_min);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
-    if (lane == 0) atomicAdd(&s_valid, my_valid);
-    __syncthreads();
-    need = min(k, s_valid);
-    collected = s_count >= need && s_count <= kTopkCap;
-    __syncthreads();
-    if (!collected) {   // rebuild the exact histogram over the whole row
-      for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
-      if (tid == 0) s_count = 0;
-      __syncthreads();
-      scan_row(c, n_songs, [&](int, unsigned long long kb, bool ok) { hist_add(s_hist, ok ? bin_of(kb) : 0u, ok, lane); });
-      __syncthreads();
-    }
   }
   if (!collected) {
     // ---- exact path: the bin holding the k-th best key from the full histogram
@@ -439,12 +553,12 @@ topk_kernel(BlendParams bp, const long long* __restrict__ sint_u, const long lon
   if (tid == 0) out_len[u] = need;
 }
 
-int launch_topk(const BlendParams& bp, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
+int launch_topk(const BlendParams& bp, const long long* te_ptr, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
                 long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
                 int* out_song, double* out_score, int* out_len, cudaStream_t st) {
   if (n_users <= 0) return 0;
   if (k <= 0 || k > kTopkCap / 2) return -2;
-  topk_kernel<<<n_users, kTopkThreads, 0, st>>>(bp, sint_u, sint_i, spitch, sel, sel_pitch_words, u0, n_songs, rsa, rsd, k,
+  topk_kernel<<<n_users, kTopkThreads, 0, st>>>(bp, te_ptr, sint_u, sint_i, spitch, sel, sel_pitch_words, u0, n_songs, rsa, rsd, k,
                                                 out_song, out_score, out_len);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -92,10 +92,11 @@ struct BlendParams {
   double prob;               // STOCH (MR:447)
   unsigned long long seed;   // STOCH: java.util.Random seed
   const long long* pair_base;  // [U+1] exclusive prefix of per-user scored-pair counts (index in MAIN:57-59 order)
+  int ubm_int_ok;            // every UBM numerator of the shard is < 2^52: (double)Sint * rsu is strictly monotone in Sint, top-k may compare integers
 };
 int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,
                        uint64_t* sel, long long sel_pitch_words, cudaStream_t st);
-int launch_topk(const BlendParams& bp, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
+int launch_topk(const BlendParams& bp, const long long* te_ptr, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
                 long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
                 int* out_song, double* out_score, int* out_len, cudaStream_t st);
 int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n, long long first_index,

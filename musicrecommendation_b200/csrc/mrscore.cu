@@ -41,6 +41,8 @@ struct mr_handle {
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
+  std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
+  bool ubm_int_ok = false;                     // every UBM numerator of the current shard is provably < 2^52 (top-k may rank the integers)
   int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
   long long pitchS = 0, pitchT = 0, spitch = 0, ldg = 0; size_t dense_bytes = 0;
   uint8_t *d_Atr = nullptr, *d_AtrT = nullptr;
@@ -572,7 +574,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
     } else {
       if (model == MODEL_AGG || model == MODEL_STOCH)
         MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, b0, nb, h->S, h->d_sel, h->sel_pitch, h->stream));
-      MR_LAUNCH(h, launch_topk(bp, need_ubm ? h->d_sint_u : nullptr, need_ibm ? h->d_sint_i : nullptr, h->spitch,
+      MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, need_ubm ? h->d_sint_u : nullptr, need_ibm ? h->d_sint_i : nullptr, h->spitch,
                                (model == MODEL_AGG || model == MODEL_STOCH) ? h->d_sel : nullptr, h->sel_pitch, b0, nb, h->S, h->d_rsa,
                                h->d_rsd, k, h->d_out_song, h->d_out_score, h->d_out_len, h->stream));
     }
@@ -591,6 +593,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
 int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long long n_total, BlendParams* bp) {
   memset(bp, 0, sizeof *bp);
   bp->model = model;
+  bp->ubm_int_ok = h->ubm_int_ok ? 1 : 0;
   if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
   if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
   if (model == MR_AGG) {
@@ -684,6 +687,9 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<float> rsvf(T), rsdf(S);
   for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); }
   for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s], kQScaleIbm); rsd[s] = rs_of(deg_song_all[s], kQInvIbm); rsdf[s] = rsf_of(deg_song_all[s]); }
+  h->song_qsum.assign(S, 0);
+  for (int s = 0; s < S; ++s)
+    for (long long i = csc_ptr[s]; i < csc_ptr[s + 1]; ++i) h->song_qsum[s] += qv[csc_idx[i]];
   // K2 work items: <= kSplitLen listeners each, longest first
   struct Item { int song; long long begin; int len; uint8_t split; };
   std::vector<Item> items;
@@ -796,6 +802,15 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   for (int u = 0; u < U; ++u) {
     rsa[u] = rs_of(deg_test[u], kQInvUbm); rsaf[u] = rsf_of(deg_test[u]);
     pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
+  }
+  {  // Sint_u[u][s] = sum_{j in I_u} Gq[j][s] <= sum_{j in I_u} song_qsum[j]
+    unsigned long long worst = 0;
+    for (int u = 0; u < U; ++u) {
+      unsigned long long sum = 0;
+      for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) sum += h->song_qsum[te_col[e]];
+      worst = std::max(worst, sum);
+    }
+    h->ubm_int_ok = worst < (1ULL << 52);
   }
   h->pair_index_base = pair_index_base;
   h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
