@@ -278,11 +278,66 @@ __device__ __forceinline__ unsigned long long proxy_of(const KeyCtx& c, long lon
   return ok ? static_cast<unsigned long long>(__double_as_longlong(blend_score(c.model, a, b, c.rsu, rd, c.alpha, c.oma, pick))) : 0ULL;
 }
 
+// Pass B of the pure IBM model.  The score (double)Sint_i * rsd[s] depends on the song, so there is no integer threshold; instead a
+// round-up fp32 product bounds the fp64 score from above — float_ru(Sint) * rsd_up[s] (rsd_up = rsd rounded up to fp32, product
+// rounded up) >= the exact product >= its fp64 rounding — and only songs whose bound reaches the threshold (rounded down to fp32)
+// are evaluated exactly.  12 bytes per song instead of 16, no fp64 work per song, and two steps of loads in flight per thread.
+__device__ __forceinline__ void ibm_collect_pass(const KeyCtx& c, const float* __restrict__ rsd_up, int n_songs, unsigned long long thr,
+                                                 unsigned long long* s_key, int* s_song, int* s_count) {
+  const int lane = threadIdx.x & 31;
+  const float t_f = __double2float_rd(__longlong_as_double(static_cast<long long>(thr)));
+  constexpr int kSteps = 2;
+  const int step = 4 * kTopkThreads;
+  for (int base0 = 0; base0 < n_songs; base0 += kSteps * step) {
+    long long b[kSteps][4]; float r[kSteps][4];
+#pragma unroll
+    for (int h = 0; h < kSteps; ++h) {
+      const int s = base0 + h * step + 4 * static_cast<int>(threadIdx.x);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { b[h][t] = -1; r[h][t] = 0.f; }
+      if (s < n_songs) {
+        const longlong2 x = __ldcs(reinterpret_cast<const longlong2*>(c.si + s)), y = __ldcs(reinterpret_cast<const longlong2*>(c.si + s + 2));
+        b[h][0] = x.x; b[h][1] = x.y; b[h][2] = y.x; b[h][3] = y.y;
+        if (s + 4 <= n_songs) { const float4 f = __ldg(reinterpret_cast<const float4*>(rsd_up + s)); r[h][0] = f.x; r[h][1] = f.y; r[h][2] = f.z; r[h][3] = f.w; }
+        else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { if (s + t < n_songs) r[h][t] = __ldg(rsd_up + s + t); else b[h][t] = -1; }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kSteps; ++h) {
+      const int s = base0 + h * step + 4 * static_cast<int>(threadIdx.x);
+      bool cand[4]; bool any = false;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { cand[t] = b[h][t] > 0 && __fmul_ru(__ll2float_ru(b[h][t]), r[h][t]) >= t_f; any = any || cand[t]; }
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          unsigned long long kb = 0;
+          if (cand[t]) kb = static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(b[h][t]), __ldg(c.rsd + s + t))));
+          const bool ok = cand[t] && kb >= thr;
+          const uint32_t m = __ballot_sync(0xffffffffu, ok);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(s_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ok) {
+              const int pos = base + __popc(m & ((1u << lane) - 1));
+              if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s + t; }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Fast path for long rows; returns true when the candidate buffer holds a superset of the top `need` keys (s_count of them).
 // *scale_out = the linear-bin scale of the exact path (from the sampled maximum), so a rejected row continues there.
 template <bool kInt>
 __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int stride, int k, int need, unsigned long long* s_key, int* s_song,
-                                               int* s_hist, unsigned long long* s_max, int* s_count, int* s_ctl, double* max_score_out) {
+                                               int* s_hist, unsigned long long* s_max, int* s_count, int* s_ctl, double* max_score_out, const float* __restrict__ rsd_up) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- A1: sampled maximum of the proxy
   unsigned long long mx = 0;
@@ -344,6 +399,11 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
   if (kInt) thr = static_cast<unsigned long long>(__float2ll_ru(__uint_as_float(static_cast<uint32_t>(lb_cut) << 17)));
   else thr = static_cast<unsigned long long>(lb_cut) << 46;
   // ---- B: one full pass, collect every song whose proxy is at or above the threshold
+  if (!kInt && c.model == MODEL_IBM && rsd_up) {
+    ibm_collect_pass(c, rsd_up, n_songs, thr, s_key, s_song, s_count);
+    __syncthreads();
+    return *s_count >= need && *s_count <= kTopkCap;
+  }
   visit_row<kInt>(c, n_songs, 1, [&](int s, const long long* a, const long long* b, const double* rd, uint64_t selw) {
     unsigned long long p[4];
     bool any = false;
@@ -405,9 +465,9 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
   if (stride > 1) {
     need = min(k, n_valid);
     if (c.model == MODEL_UBM && bp.ubm_int_ok && c.rsu > 0.0)
-      collected = topk_fast_path<true>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score);
+      collected = topk_fast_path<true>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score, nullptr);
     else
-      collected = topk_fast_path<false>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score);
+      collected = topk_fast_path<false>(c, n_songs, stride, k, need, s_key, s_song, s_hist, s_max, &s_count, s_ctl, &max_score, bp.rsd_up);
     __syncthreads();
   } else {
     // ---- short rows: exact maximum

@@ -125,13 +125,13 @@ template <> __device__ __forceinline__ RowWords<4> ld_row_words<4>(const void* p
 // A group's segments and entries (head row index, weight) are contiguous in the group-ordered arrays the host built; the CTA stages
 // them in shared memory with one coalesced round of loads, so the inner loop's only global accesses are the row loads themselves
 // (no dependent index -> row chain per round).
-template <bool kIbm, int W>
-__global__ void __launch_bounds__(256, kHeadCtasPerSm)
+template <bool kIbm, int W, int kRowsI = 2>
+__global__ void __launch_bounds__(256, (kIbm && kRowsI > 2) ? 5 : kHeadCtasPerSm)
 head_rowsum_kernel(const int4* __restrict__ grp_hdr, const int4* __restrict__ seg, const int* __restrict__ ge_row,
                    const uint32_t* __restrict__ ge_q, int seg_cap, int ent_cap, const uint16_t* __restrict__ g16,
                    const uint32_t* __restrict__ gq32, long long pitch, int n_songs, long long* __restrict__ sint, long long spitch) {
   constexpr int kVec = kIbm ? 2 * W : W;
-  constexpr int kRows = kIbm ? (W == 1 ? 4 : 2) : (W == 4 ? 4 : 8);   // rows in flight per thread
+  constexpr int kRows = kIbm ? (W == 1 ? 4 : kRowsI) : (W == 4 ? 4 : 8);   // rows in flight per thread
   extern __shared__ int4 s_dyn[];
   int4* s_seg = s_dyn;                                                // [seg_cap]
   int* s_row = reinterpret_cast<int*>(s_dyn + seg_cap);               // [ent_cap]
@@ -192,6 +192,8 @@ int launch_head_rowsum(int model, int words, int threads, const int4* grp_hdr, i
   if (smem > 48 * 1024) return -3;
 #define MR_HR(IBM, W) head_rowsum_kernel<IBM, W><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch)
   if (model == 1) { if (words == 4) MR_HR(false, 4); else if (words == 2) MR_HR(false, 2); else if (words == 1) MR_HR(false, 1); else return -2; }
+  else if (model == 2 && words == 4 && getenv("MRSCORE_IBM_ROWS4")) head_rowsum_kernel<true, 4, 4><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch);
+  else if (model == 2 && words == 2 && getenv("MRSCORE_IBM_ROWS4")) head_rowsum_kernel<true, 2, 8><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch);
   else if (model == 2) { if (words == 4) MR_HR(true, 4); else if (words == 2) MR_HR(true, 2); else if (words == 1) MR_HR(true, 1); else return -2; }
   else return -2;
 #undef MR_HR
@@ -284,9 +286,11 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
 
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
-                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, int num_sms, cudaStream_t st) {
-  if (e1 <= e0) return 0;
-  const int grid = num_sms * 8;
+                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs, cudaStream_t st) {
+  if (e1 <= e0 || n_pairs <= 0) return 0;
+  // one warp per (entry, listener) pair in short-lived CTAs (measured 25 % faster than a persistent grid-stride grid: the block
+  // scheduler balances the 1..4000-song listeners better than a static stride does)
+  const int grid = static_cast<int>(std::min<long long>((n_pairs + 7) / 8, 1LL << 30));
   if (models == 1) tail_scatter_kernel<1><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
   else if (models == 2) tail_scatter_kernel<2><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
   else tail_scatter_kernel<3><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);

@@ -8,7 +8,7 @@ namespace mr {
 constexpr int kUserBatch = 128;   // test users per batch of the user-space engine = UMMA M
 constexpr int kHeadCtasPerSm = 8;  // head_rowsum: resident 256-thread CTAs per SM the UBM pass is compiled for (32 registers per thread)
 constexpr int kDenseChunk = 1184;  // rows per device->host chunk of mr_score_dense
-constexpr int kTailSubBatch = 296; // tail scatter runs per 296 users so its atomics stay within a ~1.8 GB slice of the Sint panels
+constexpr int kTailSubBatch = 592; // tail scatter runs per 592 users so its atomics stay within a ~1.8 GB slice of a Sint panel
 // Count panels K1 hands to K2, train-user-major so that one gathered row serves the whole 128-user batch in one coalesced read:
 //   UBM  u16 Ct[T][128]   256-byte rows     IBM (user space)  u32 Wi[T][128]   512-byte rows
 // (A sub-panel-major variant with 32-byte, L2-resident rows was measured 1.7-1.9x slower on B200: random 32-byte sector
@@ -78,7 +78,7 @@ int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, co
                       long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st);
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
-                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, int num_sms, cudaStream_t st);
+                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs, cudaStream_t st);
 
 // ---- K3 (k3_topk.cu)
 int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
@@ -92,6 +92,7 @@ struct BlendParams {
   double prob;               // STOCH (MR:447)
   unsigned long long seed;   // STOCH: java.util.Random seed
   const long long* pair_base;  // [U+1] exclusive prefix of per-user scored-pair counts (index in MAIN:57-59 order)
+  const float* rsd_up;       // [S] rsd rounded up to fp32 (upper bounds for the IBM pre-filter of the top-k select), or null
   int ubm_int_ok;            // every UBM numerator of the shard is < 2^52: (double)Sint * rsu is strictly monotone in Sint, top-k may compare integers
 };
 int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,

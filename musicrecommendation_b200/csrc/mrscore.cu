@@ -39,7 +39,7 @@ struct mr_handle {
   // train
   int T = 0, S = 0; long long nnz_tr = 0; bool loaded = false;
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
-  uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr;
+  uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
   std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
   bool ubm_int_ok = false;                     // every UBM numerator of the current shard is provably < 2^52 (top-k may rank the integers)
@@ -57,7 +57,7 @@ struct mr_handle {
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
   long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
   long long *d_hu_ptr = nullptr; int *d_hu_row = nullptr, *d_hu_song = nullptr; uint32_t* d_hu_q = nullptr;
-  int *d_tu_user = nullptr, *d_tu_song = nullptr; long long* d_tu_lptr = nullptr; std::vector<long long> h_tu_ptr; long long n_head_entries = 0, n_tail_entries = 0;
+  int *d_tu_user = nullptr, *d_tu_song = nullptr; long long* d_tu_lptr = nullptr; std::vector<long long> h_tu_ptr, h_tu_lptr; long long n_head_entries = 0, n_tail_entries = 0;
   // test shard (freed / reallocated by mr_set_test_users)
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
@@ -501,12 +501,14 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
                                          h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
       }
+      // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users)
+      static const int tail_sub = getenv("MRSCORE_TAIL_SUB") ? std::max(8, atoi(getenv("MRSCORE_TAIL_SUB"))) : kTailSubBatch;
       PhaseTimer t(h, MR_T_TAIL_SCATTER);
-      for (int s0 = 0; s0 < nb; s0 += kTailSubBatch) {
-        const int sn = std::min(kTailSubBatch, nb - s0);
+      for (int s0 = 0; s0 < nb; s0 += tail_sub) {
+        const int sn = std::min(tail_sub, nb - s0);
         const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
         MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                         h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->num_sms, h->stream));
+                                         h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
       }
     } else if (need_ubm) {
       int rc = count_ubm_batch(h, b0, nb);
@@ -594,6 +596,7 @@ int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long
   memset(bp, 0, sizeof *bp);
   bp->model = model;
   bp->ubm_int_ok = h->ubm_int_ok ? 1 : 0;
+  bp->rsd_up = h->d_rsd_up;
   if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
   if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
   if (model == MR_AGG) {
@@ -713,6 +716,12 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if ((rc = dev_upload(h, &h->d_qv, qv.data(), qv.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_qd, qd.data(), qd.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_rsd, rsd.data(), rsd.size(), h->allocs))) return rc;
+  {  // rsd rounded UP to fp32: the top-k select bounds IBM scores from above with it
+    std::vector<float> up(S);
+    for (int s = 0; s < S; ++s) { float f = static_cast<float>(rsd[s]); if (static_cast<double>(f) < rsd[s]) f = std::nextafterf(f, INFINITY); up[s] = f; }
+    if ((rc = dev_upload(h, &h->d_rsd_up, up.data(), up.size(), h->allocs))) return rc;
+    MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   if ((rc = dev_upload(h, &h->d_rsv_f, rsvf.data(), rsvf.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_rsd_f, rsdf.data(), rsdf.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_item_song, it_song.data(), it_song.size(), h->allocs))) return rc;
@@ -859,6 +868,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     if ((rc = slot_upload(h, mr_handle::SL_TU_USER, &h->d_tu_user, tu_user.data(), tu_user.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_TU_SONG, &h->d_tu_song, tu_song.data(), tu_song.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, tu_lptr.data(), tu_lptr.size()))) return rc;
+    h->h_tu_lptr = tu_lptr;
     h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
     if ((rc = plan_item_batches(h, hu_ptr, hu_row, hu_q))) return rc;
