@@ -134,19 +134,19 @@ head_rowsum_kernel(const int4* __restrict__ grp_hdr, const int4* __restrict__ se
   constexpr int kRows = kIbm ? (W == 1 ? 4 : kRowsI) : (W == 4 ? 4 : 8);   // rows in flight per thread
   extern __shared__ int4 s_dyn[];
   int4* s_seg = s_dyn;                                                // [seg_cap]
-  int* s_row = reinterpret_cast<int*>(s_dyn + seg_cap);               // [ent_cap]
+  uint32_t* s_row = reinterpret_cast<uint32_t*>(s_dyn + seg_cap);     // [ent_cap]
+  const uint32_t rb64 = static_cast<uint32_t>(pitch * (kIbm ? 2 : 4) / 64);
   uint32_t* s_q = reinterpret_cast<uint32_t*>(s_row + ent_cap);       // [ent_cap] (IBM only)
   const int4 hd = __ldg(grp_hdr + blockIdx.x);                        // x: first segment, y: segments, z: first entry, w: entries
   for (int i = threadIdx.x; i < hd.y; i += blockDim.x) s_seg[i] = __ldg(seg + hd.x + i);
   for (int i = threadIdx.x; i < hd.w; i += blockDim.x) {
-    s_row[i] = __ldg(ge_row + hd.z + i);
+    s_row[i] = __ldg(ge_row + hd.z + i) * rb64;                        // row offset in 64-byte units (rows are multiples of 64 bytes; < 2^32 for any HBM size)
     if (kIbm) s_q[i] = __ldg(ge_q + hd.z + i);
   }
   __syncthreads();
   const int s = kVec * (blockIdx.y * blockDim.x + threadIdx.x);
   if (s >= n_songs) return;
   const char* base = kIbm ? reinterpret_cast<const char*>(g16 + s) : reinterpret_cast<const char*>(gq32 + s);
-  const long long row_bytes = pitch * (kIbm ? 2 : 4);
   for (int gi = 0; gi < hd.y; ++gi) {
     const int4 sg = s_seg[gi];                                        // x: Sint row, y..z: staged entries, w: accumulate into a pre-zeroed row
     unsigned long long acc[kVec];
@@ -163,11 +163,11 @@ head_rowsum_kernel(const int4* __restrict__ grp_hdr, const int4* __restrict__ se
     for (; i + kRows <= sg.z; i += kRows) {
       RowWords<W> c[kRows];
 #pragma unroll
-      for (int t = 0; t < kRows; ++t) c[t] = ld_row_words<W>(base + static_cast<long long>(s_row[i + t]) * row_bytes);
+      for (int t = 0; t < kRows; ++t) c[t] = ld_row_words<W>(base + static_cast<unsigned long long>(s_row[i + t]) * 64u);
 #pragma unroll
       for (int t = 0; t < kRows; ++t) add_row(c[t], kIbm ? s_q[i + t] : 0u);
     }
-    for (; i < sg.z; ++i) add_row(ld_row_words<W>(base + static_cast<long long>(s_row[i]) * row_bytes), kIbm ? s_q[i] : 0u);
+    for (; i < sg.z; ++i) add_row(ld_row_words<W>(base + static_cast<unsigned long long>(s_row[i]) * 64u), kIbm ? s_q[i] : 0u);
     unsigned long long* o = reinterpret_cast<unsigned long long*>(sint) + static_cast<long long>(sg.x) * spitch + s;
     if (sg.w) {
 #pragma unroll
