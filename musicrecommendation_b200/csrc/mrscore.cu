@@ -399,7 +399,7 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
     const size_t per_row = static_cast<size_t>(h->spitch) * 16 + static_cast<size_t>(h->sel_pitch) * 8;
     size_t avail = free_b + h->slot_cap[mr_handle::SL_SINT_U] + h->slot_cap[mr_handle::SL_SINT_I] + h->slot_cap[mr_handle::SL_SEL];
-    size_t reserve = (3ULL << 30) + static_cast<size_t>(kDenseChunk) * h->S * 8;
+    size_t reserve = (6ULL << 30) + static_cast<size_t>(kDenseChunk) * h->S * 8;   // left for the caller's context: torch, NCCL buffers, gathered top-k blocks
     if (!h->head_ready) reserve += static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch * 6 + (1ULL << 30);   // head rows + staging come later
     long long max_rows = avail > reserve ? static_cast<long long>((avail - reserve) / per_row) : 0;
     max_rows = std::max<long long>(max_rows, kUserBatch);
