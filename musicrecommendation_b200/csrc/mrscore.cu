@@ -399,7 +399,7 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
     const size_t per_row = static_cast<size_t>(h->spitch) * 16 + static_cast<size_t>(h->sel_pitch) * 8;
     size_t avail = free_b + h->slot_cap[mr_handle::SL_SINT_U] + h->slot_cap[mr_handle::SL_SINT_I] + h->slot_cap[mr_handle::SL_SEL];
-    size_t reserve = (6ULL << 30) + static_cast<size_t>(kDenseChunk) * h->S * 8;   // left for the caller's context: torch, NCCL buffers, gathered top-k blocks
+    size_t reserve = 6ULL << 30;   // left for the caller's context (torch, NCCL buffers, gathered top-k blocks) and small workspaces
     if (!h->head_ready) reserve += static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch * 6 + (1ULL << 30);   // head rows + staging come later
     long long max_rows = avail > reserve ? static_cast<long long>((avail - reserve) / per_row) : 0;
     max_rows = std::max<long long>(max_rows, kUserBatch);
@@ -768,7 +768,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     if (const char* e = getenv("MRSCORE_HEAD_MIN_DEG")) min_deg = std::max(1LL, atoll(e));
     size_t free_b = 0, total_b = 0;
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-    const long long max_rows = static_cast<long long>((free_b / 2) / (static_cast<size_t>(h->spitch) * 6));   // packed rows: 6 B per entry
+    const long long max_rows = static_cast<long long>((free_b / 100 * 47) / (static_cast<size_t>(h->spitch) * 6));   // packed rows: 6 B per entry; the rest holds the Sint panels
     std::vector<int> order(S);
     for (int s = 0; s < S; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return csc_ptr[a + 1] - csc_ptr[a] > csc_ptr[b + 1] - csc_ptr[b]; });
