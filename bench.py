@@ -298,7 +298,7 @@ def main():
             check(lib.mr_topk(h, model, 0.0, 0, k, p(out[0][1]), p(out[1][1]), p(out[2][1])))
             if world > 1:   # the reference's `.collect` (DIST:451-478): all-gather the fixed-size top-k blocks over NCCL
                 torch.cuda.current_stream().wait_stream(stream)
-                gather_topk(*mr.topk_device_tensors(k), U * world, world, rank)
+                gather_topk(*mr.topk_device_tensors(k), U * world, world, rank, reuse_buffers=True)
         if verbose:
             log(f"[rank {rank}] e2e step: mr_set_test_users {1e3 * (t_b - t_a):.1f} ms, 2 x mr_topk {1e3 * (time.perf_counter() - t_b):.1f} ms")
 

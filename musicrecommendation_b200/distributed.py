@@ -30,9 +30,14 @@ def pair_index_bases(ds: Dataset, world: int) -> tuple[np.ndarray, int]:
     return starts, int(prefix[-1])
 
 
-def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, group=None):
+_GATHER_BUFFERS: dict = {}
+
+
+def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, group=None, reuse_buffers: bool = False):
     """All-gather the per-shard top-k blocks into the full [U, k] result (the reference's `.collect`).  Accepts numpy arrays or
-    torch tensors (CPU for gloo, CUDA for nccl); returns torch tensors on the same device."""
+    torch tensors (CPU for gloo, CUDA for nccl); returns torch tensors on the same device.  Equal shards (the usual case) are gathered
+    by one `all_gather_into_tensor` per array straight into the result; with reuse_buffers=True that result lives in a per-shape
+    buffer that the next call overwrites (a steady-state scoring loop then allocates nothing)."""
     import torch
     import torch.distributed as dist
     song = torch.as_tensor(song)
@@ -40,9 +45,9 @@ def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, 
     length = torch.as_tensor(length)
     if world == 1:
         return song, score, length
-    k = song.shape[1]
     sizes = [shard_range(n_users_total, r, world) for r in range(world)]
     max_n = max(b - a for a, b in sizes)
+    equal = all(b - a == max_n for a, b in sizes)
 
     def pad(t, fill):
         if t.shape[0] == max_n:
@@ -53,9 +58,18 @@ def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, 
     outs = []
     for t, fill in ((song, -1), (score, 0.0), (length, 0)):
         p = pad(t, fill)
-        buf = [torch.empty_like(p) for _ in range(world)]
-        dist.all_gather(buf, p, group=group)
-        outs.append(torch.cat([b[: hi - lo] for b, (lo, hi) in zip(buf, sizes)]))
+        shape = (world * max_n,) + tuple(p.shape[1:])
+        key = (str(p.device), p.dtype, shape)
+        full = _GATHER_BUFFERS.get(key) if reuse_buffers else None
+        if full is None:
+            full = torch.empty(shape, dtype=p.dtype, device=p.device)
+            if reuse_buffers:
+                _GATHER_BUFFERS[key] = full
+        dist.all_gather_into_tensor(full, p, group=group)
+        if equal:
+            outs.append(full)
+        else:
+            outs.append(torch.cat([full[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]))
     return tuple(outs)
 
 

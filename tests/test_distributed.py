@@ -46,6 +46,10 @@ def _worker(rank, world, port, out_dir):
         song, score, ln = oracle.topk(model, 50)
         g = gather_topk(song, score, ln, ds.U, world, rank)
         results[name] = [t.numpy() for t in g]
+        if kind is None:   # equal shards (first 5 users of each rank): one all_gather_into_tensor per array into a reused buffer
+            for _ in range(2):
+                g = gather_topk(song[:5], score[:5], ln[:5], 10, world, rank, reuse_buffers=True)
+            results["eq"] = [t.numpy().copy() for t in g]
     # K-split of the item-item Gram: partial panels of the ranks' train-user shards, summed and row-scattered
     part = torch.from_numpy(oracle.gram_rows(split_train_users(ds, rank, world), np.arange(0, 64)))
     mine = reduce_scatter_rows(part, world, rank)
@@ -75,6 +79,11 @@ def test_two_process_gloo_gather_matches_single_process(tmp_path, oracle_lib):
     full = oracle_lib.gram_rows(ds, np.arange(0, 64))
     for r in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / f"gram_rows_rank{r}.npy"), full[r * 32:(r + 1) * 32])
+    ws, wv, wl = oracle_lib.topk(ubm, 50)
+    pick = np.r_[0:5, 6:11]                      # shard_range(11, r, 2) = [0,6), [6,11)
+    np.testing.assert_array_equal(got["eq_0"], ws[pick])
+    np.testing.assert_array_equal(got["eq_1"], wv[pick])
+    np.testing.assert_array_equal(got["eq_2"], wl[pick])
     for name, model in want.items():
         ws, wv, wl = oracle_lib.topk(model, 50)
         np.testing.assert_array_equal(got[f"{name}_0"], ws)
