@@ -41,6 +41,7 @@ struct mr_handle {
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
+  std::vector<uint32_t> h_qd;                  // per song q_26(d_s) (host copy: mr_set_test_users tags head entries with it)
   std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
   bool ubm_int_ok = false;                     // every UBM numerator of the current shard is provably < 2^52 (top-k may rank the integers)
   int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
@@ -690,6 +691,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<float> rsvf(T), rsdf(S);
   for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); }
   for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s], kQScaleIbm); rsd[s] = rs_of(deg_song_all[s], kQInvIbm); rsdf[s] = rsf_of(deg_song_all[s]); }
+  h->h_qd = qd;
   h->song_qsum.assign(S, 0);
   for (int s = 0; s < S; ++s)
     for (long long i = csc_ptr[s]; i < csc_ptr[s + 1]; ++i) h->song_qsum[s] += qv[csc_idx[i]];
@@ -852,10 +854,11 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     std::vector<long long> hu_ptr(static_cast<size_t>(U) + 1, 0);
     std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q; std::vector<long long> tu_lptr(1, 0);
     h->h_tu_ptr.assign(static_cast<size_t>(U) + 1, 0);
+    hu_row.reserve(static_cast<size_t>(nnz)); hu_song.reserve(static_cast<size_t>(nnz)); hu_q.reserve(static_cast<size_t>(nnz));
     for (int u = 0; u < U; ++u) {
       for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) {
         const int j = te_col[e]; const int hr = h->head_index[j];
-        if (hr >= 0) { hu_row.push_back(hr); hu_song.push_back(j); hu_q.push_back(q_of(h->deg_song[j], kQScaleIbm)); }
+        if (hr >= 0) { hu_row.push_back(hr); hu_song.push_back(j); hu_q.push_back(h->h_qd[j]); }
         else { tu_user.push_back(u); tu_song.push_back(j); tu_lptr.push_back(tu_lptr.back() + h->deg_song_train[j]); }
       }
       hu_ptr[u + 1] = static_cast<long long>(hu_row.size());
