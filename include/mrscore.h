@@ -141,6 +141,26 @@ int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int
  * NCCL without a host round trip (the reference's `.collect`, DIST:451-478).  Valid until the next call on the handle. */
 int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** len);
 
+/* ---- ingest: `new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12, 26-91) on the GPU ----------------------------------
+ * The three TSV files as byte buffers (`user \t song \t count` per line, third field ignored, MR:35) become the int-id data model
+ * mr_load takes: ids assigned in ascending String.compareTo order per id space (train users; test users; songs of the train and the test
+ * file, MR:38, 51, 58), sorted de-duplicated CSR rows, and the `.length` degrees that count duplicate rows (MR:40-41, 147, 237).  Label
+ * rows of users outside the test file are dropped; label songs that occur nowhere else get ids >= n_songs (they score 0 in MR:521-639).
+ * A line without exactly 3 fields (after Java's split dropped trailing empty ones) is the reference's scala.MatchError -> MR_ERR_BAD_ARG
+ * naming the line.  The result lives in host memory owned by the library until mr_ingest_free.  No CPU fallback. */
+typedef struct mr_ingest mr_ingest;
+enum { MR_ING_TR_PTR = 0, MR_ING_TR_COL, MR_ING_TE_PTR, MR_ING_TE_COL, MR_ING_LAB_PTR, MR_ING_LAB_COL,      /* int64 [rows+1] / int32 [nnz] */
+       MR_ING_DEG_TRAIN, MR_ING_DEG_TEST, MR_ING_DEG_SONG,                                                   /* int32 */
+       MR_ING_TRAIN_USER_CHARS, MR_ING_TRAIN_USER_OFF, MR_ING_TEST_USER_CHARS, MR_ING_TEST_USER_OFF,           /* id -> string tables: bytes + int64 [n+1] */
+       MR_ING_SONG_CHARS, MR_ING_SONG_OFF,                                                                   /* n_songs + n_label_only entries */
+       MR_ING_TIMING_MS };                                                                                   /* double [8]: h2d, lines+parse, users, songs, host sort, csr, -, total */
+int mr_ingest_tsv(int device, const char* train, uint64_t train_len, const char* test, uint64_t test_len, const char* labels,
+                  uint64_t labels_len, mr_ingest** out);
+const char* mr_ingest_error(const mr_ingest* g);
+int mr_ingest_dims(const mr_ingest* g, int32_t* n_train, int32_t* n_test, int32_t* n_songs, int32_t* n_label_only_songs);
+int mr_ingest_get(const mr_ingest* g, int which, const void** ptr, int64_t* n_elems);
+void mr_ingest_free(mr_ingest* g);
+
 /* Introspection used by bench.py / tests. */
 enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5,
        MR_T_PRECOMPUTE = 6, MR_T_HEAD_ROWSUM = 7, MR_T_TAIL_SCATTER = 8, MR_T_N = 9 };

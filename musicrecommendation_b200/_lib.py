@@ -12,12 +12,15 @@ MR_UBM, MR_IBM, MR_LC, MR_AGG, MR_STOCH = range(5)
 MR_ENGINE_AUTO, MR_ENGINE_TENSOR, MR_ENGINE_SPARSE = 0, 1, 2
 MR_PROFILE = 4
 MR_SPACE_AUTO, MR_SPACE_USER, MR_SPACE_ITEM = 0, 8, 16
+(MR_ING_TR_PTR, MR_ING_TR_COL, MR_ING_TE_PTR, MR_ING_TE_COL, MR_ING_LAB_PTR, MR_ING_LAB_COL, MR_ING_DEG_TRAIN, MR_ING_DEG_TEST, MR_ING_DEG_SONG,
+ MR_ING_TRAIN_USER_CHARS, MR_ING_TRAIN_USER_OFF, MR_ING_TEST_USER_CHARS, MR_ING_TEST_USER_OFF, MR_ING_SONG_CHARS, MR_ING_SONG_OFF, MR_ING_TIMING_MS) = range(16)
 TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
 
 # every symbol include/mrscore.h declares
 SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device", "mr_gram_rows_scatter", "mr_peer_alloc", "mr_peer_open", "mr_peer_close",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_evaluate_dense", "mr_topk", "mr_topk_device",
-           "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream"]
+           "mr_topk_fetch", "mr_topk_device_ptrs", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream",
+           "mr_ingest_tsv", "mr_ingest_error", "mr_ingest_dims", "mr_ingest_get", "mr_ingest_free"]
 
 _lib = None
 
@@ -69,5 +72,12 @@ def load():
     lib.mr_get_info.argtypes = [vp, vp, i32]
     lib.mr_stream.argtypes = [vp]
     lib.mr_stream.restype = vp
+    lib.mr_ingest_tsv.argtypes = [i32, vp, u64, vp, u64, vp, u64, C.POINTER(vp)]
+    lib.mr_ingest_error.argtypes = [vp]
+    lib.mr_ingest_error.restype = C.c_char_p
+    lib.mr_ingest_dims.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.mr_ingest_get.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    lib.mr_ingest_free.argtypes = [vp]
+    lib.mr_ingest_free.restype = None
     _lib = lib
     return lib

@@ -117,13 +117,68 @@ def dataset_from_streams(train, test, labels) -> Dataset:
                    train_users, test_users, songs + label_only, {"source": "tsv"})
 
 
+def _read_bytes(f) -> bytes:
+    if isinstance(f, (bytes, bytearray, memoryview)):
+        return bytes(f)
+    if isinstance(f, str) or hasattr(f, "__fspath__"):
+        with open(f, "rb") as fh:
+            return fh.read()
+    data = f.read()
+    return data.encode("utf-8") if isinstance(data, str) else bytes(data)
+
+
+def dataset_from_streams_native(train, test, labels, device: int = 0, with_strings: bool = True) -> Dataset:
+    """The same ingest on the GPU (`mr_ingest_tsv`, csrc/k6_ingest.cu): the three TSV files as bytes -> int-id CSR, ids in ascending
+    string order, `.length` degrees.  Same result as dataset_from_streams (tests/test_gpu_parity.py compares them field by field);
+    a malformed line raises ValueError like the host path.  `timing_ms` of the stages is kept in Dataset.meta."""
+    lib = _lib.load()
+    bufs = [_read_bytes(f) for f in (train, test, labels)]
+    g = C.c_void_p()
+    rc = lib.mr_ingest_tsv(device, bufs[0], len(bufs[0]), bufs[1], len(bufs[1]), bufs[2], len(bufs[2]), C.byref(g))
+    try:
+        if rc != _lib.MR_OK:
+            msg = (lib.mr_ingest_error(g) or b"").decode()
+            if rc == _lib.MR_ERR_BAD_ARG and msg.startswith("scala.MatchError"):
+                raise ValueError(msg)
+            raise _lib.MrError(rc, msg)
+        dims = [C.c_int32() for _ in range(4)]
+        lib.mr_ingest_dims(g, *[C.byref(d) for d in dims])
+        T, U, S, n_extra = (d.value for d in dims)
+
+        def get(which, dtype):
+            ptr, n = C.c_void_p(), C.c_int64()
+            lib.mr_ingest_get(g, which, C.byref(ptr), C.byref(n))
+            if n.value == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n.value,)).copy()
+
+        def table(chars_id, off_id):
+            if not with_strings:
+                return None
+            chars = get(chars_id, np.uint8).tobytes()
+            off = get(off_id, np.int64)
+            return [chars[off[i]:off[i + 1]].decode("utf-8") for i in range(len(off) - 1)]
+
+        return Dataset(T, U, S, get(_lib.MR_ING_TR_PTR, np.int64), get(_lib.MR_ING_TR_COL, np.int32), get(_lib.MR_ING_TE_PTR, np.int64),
+                       get(_lib.MR_ING_TE_COL, np.int32), get(_lib.MR_ING_LAB_PTR, np.int64), get(_lib.MR_ING_LAB_COL, np.int32),
+                       get(_lib.MR_ING_DEG_TRAIN, np.int32), get(_lib.MR_ING_DEG_TEST, np.int32), get(_lib.MR_ING_DEG_SONG, np.int32),
+                       table(_lib.MR_ING_TRAIN_USER_CHARS, _lib.MR_ING_TRAIN_USER_OFF), table(_lib.MR_ING_TEST_USER_CHARS, _lib.MR_ING_TEST_USER_OFF),
+                       table(_lib.MR_ING_SONG_CHARS, _lib.MR_ING_SONG_OFF),
+                       {"source": "tsv-native", "label_only_songs": n_extra, "timing_ms": dict(zip(
+                           ["h2d", "lines_parse", "unique_users", "unique_songs", "host_sort", "csr", "unused", "total"], get(_lib.MR_ING_TIMING_MS, np.float64).tolist()))})
+    finally:
+        lib.mr_ingest_free(g)
+
+
 class MusicRecommender:
     """`new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12).  Also accepts a ready `Dataset`."""
 
     def __init__(self, trainFile, testFile=None, testLabelsFile=None, device: int = 0, engine: int = _lib.MR_ENGINE_AUTO,
-                 profile: bool = False, space: int = _lib.MR_SPACE_AUTO):
+                 profile: bool = False, space: int = _lib.MR_SPACE_AUTO, ingest: str = "host"):
         if isinstance(trainFile, Dataset):
             ds = trainFile
+        elif ingest == "native":
+            ds = dataset_from_streams_native(trainFile, testFile, testLabelsFile, device=device)
         else:
             def op(f):
                 return open(f, "r", encoding="utf-8") if isinstance(f, (str, bytes)) or hasattr(f, "__fspath__") else f

@@ -95,3 +95,12 @@ def test_model_tuples_order():
     m = recommender.Model(scores, ds.test_users, ds.songs)
     assert [(u, s) for u, (s, _) in m.tuples()] == [("X", "s2"), ("X", "s3"), ("Y", "s1"), ("Y", "s3"), ("Y", "s4")]
     assert len(m) == 5
+
+
+def test_native_ingest_has_no_cpu_fallback(mrlib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MrError) as ei:
+        recommender.dataset_from_streams_native(b"A\ts1\t1\n", b"X\ts1\t1\n", b"X\ts2\t1\n")
+    assert ei.value.code == _lib.MR_ERR_CUDA and "no CPU fallback" in ei.value.msg
