@@ -3,7 +3,7 @@
 package music_recommandation
 
 import com.sun.jna.{Library, Native, Pointer}
-import com.sun.jna.ptr.PointerByReference
+import com.sun.jna.ptr.{IntByReference, LongByReference, PointerByReference}
 
 trait MrScore extends Library {
   def mr_create(out: PointerByReference, deviceIds: Array[Int], nDevices: Int, flags: Int): Int
@@ -18,6 +18,15 @@ trait MrScore extends Library {
                      out: Array[Double], nPairs: Long, firstIndex: Long, nTotal: Long): Int
   def mr_topk(h: Pointer, model: Int, param: Double, seed: Long, k: Int, outSong: Array[Int], outScore: Array[Double],
               outLen: Array[Int]): Int
+  def mr_evaluate_dense(h: Pointer, scoresUxS: Array[Double], nUsers: Int, nSongs: Int, labRowPtr: Array[Long], labCol: Array[Int],
+                        nThresholds: Int, outMap: Array[Double]): Int
+  // TSV -> int-id data model on the GPU (MusicRecommender.scala:26-91); the result object is read with mr_ingest_get(which = MR_ING_*)
+  def mr_ingest_tsv(device: Int, train: Array[Byte], trainLen: Long, test: Array[Byte], testLen: Long, labels: Array[Byte],
+                    labelsLen: Long, out: PointerByReference): Int
+  def mr_ingest_error(g: Pointer): String
+  def mr_ingest_dims(g: Pointer, nTrain: IntByReference, nTest: IntByReference, nSongs: IntByReference, nLabelOnly: IntByReference): Int
+  def mr_ingest_get(g: Pointer, which: Int, ptr: PointerByReference, nElems: LongByReference): Int
+  def mr_ingest_free(g: Pointer): Unit
 }
 
 object NativeScorer {
