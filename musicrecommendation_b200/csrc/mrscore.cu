@@ -33,6 +33,7 @@ constexpr int kSplitLen = 4096;   // listeners per K2 work item
 struct mr_handle {
   int device = 0; int num_sms = 148; unsigned flags = 0; int engine = MR_ENGINE_AUTO;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_slice = nullptr;   // mr_topk streams finished slices of the result to the host beside the compute
   std::string err;
   long long launches = 0; size_t dev_bytes = 0;
   std::vector<void*> allocs;          // everything freed in mr_destroy
@@ -472,6 +473,7 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
 }
 
 enum RunMode { RUN_TOPK, RUN_DENSE, RUN_COUNTS_UBM, RUN_SIM_UBM };
+struct TopkHostOut { int32_t* song; double* score; int32_t* len; };   // RUN_TOPK: caller buffers the finished slices are copied into
 
 int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode mode, void* host_out) {
   const bool need_ubm = model != MODEL_IBM;
@@ -502,15 +504,40 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
                                          h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
       }
-      // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users)
+      // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users);
+      // in top-k mode the slice is masked and selected right away, and its rows of the result go to the caller's buffers on the copy
+      // stream while the next slice computes
       static const int tail_sub = getenv("MRSCORE_TAIL_SUB") ? std::max(8, atoi(getenv("MRSCORE_TAIL_SUB"))) : kTailSubBatch;
-      PhaseTimer t(h, MR_T_TAIL_SCATTER);
+      const bool sel_needed = model == MODEL_AGG || model == MODEL_STOCH;
+      const TopkHostOut* ho = mode == RUN_TOPK ? static_cast<const TopkHostOut*>(host_out) : nullptr;
       for (int s0 = 0; s0 < nb; s0 += tail_sub) {
         const int sn = std::min(tail_sub, nb - s0);
-        const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
-        MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                         h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
+        {
+          PhaseTimer t(h, MR_T_TAIL_SCATTER);
+          const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
+          MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
+                                           h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
+        }
+        if (mode != RUN_TOPK) continue;
+        PhaseTimer t(h, MR_T_TOPK);
+        long long* su = need_ubm ? h->d_sint_u + static_cast<long long>(s0) * h->spitch : nullptr;
+        long long* si = need_ibm ? h->d_sint_i + static_cast<long long>(s0) * h->spitch : nullptr;
+        uint64_t* sel = sel_needed ? h->d_sel + static_cast<long long>(s0) * h->sel_pitch : nullptr;
+        const int u0 = b0 + s0;
+        MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_col, u0, sn, su, si, h->spitch, h->stream));
+        if (sel_needed) MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, u0, sn, h->S, sel, h->sel_pitch, h->stream));
+        MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, su, si, h->spitch, sel, h->sel_pitch, u0, sn, h->S, h->d_rsa, h->d_rsd, k, h->d_out_song,
+                                 h->d_out_score, h->d_out_len, h->stream));
+        if (ho) {
+          MR_CUDA(h, cudaEventRecord(h->ev_slice, h->stream));
+          MR_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_slice, 0));
+          const size_t o = static_cast<size_t>(u0) * k, n = static_cast<size_t>(sn) * k;
+          MR_CUDA(h, cudaMemcpyAsync(ho->song + o, h->d_out_song + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+          MR_CUDA(h, cudaMemcpyAsync(ho->score + o, h->d_out_score + o, n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+          MR_CUDA(h, cudaMemcpyAsync(ho->len + u0, h->d_out_len + u0, static_cast<size_t>(sn) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
       }
+      if (mode == RUN_TOPK) continue;   // the batch is finished; RUN_DENSE continues below on the whole batch
     } else if (need_ubm) {
       int rc = count_ubm_batch(h, b0, nb);
       if (rc) return rc;
@@ -638,6 +665,8 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
   h->engine = flags & MR_ENGINE_MASK;
   h->space_flag = flags & MR_SPACE_MASK;
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  MR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_slice, cudaEventDisableTiming));
   MR_CUDA(h, cudaEventCreate(&h->ev[0]));
   MR_CUDA(h, cudaEventCreate(&h->ev[1]));
   return MR_OK;
@@ -646,6 +675,8 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
 void mr_destroy(mr_handle* h) {
   if (!h) return;
   if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->ev_slice) cudaEventDestroy(h->ev_slice);
   for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);
   free_list(h->allocs);
   if (h->h_carry_seen) cudaFreeHost(h->h_carry_seen);
@@ -1129,7 +1160,7 @@ int mr_evaluate_dense(mr_handle* h, const double* scores_UxS, int n_users, int n
   return MR_OK;
 }
 
-int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) {
+static int topk_impl(mr_handle* h, int model, double param, uint64_t seed, int k, const TopkHostOut* ho) {
   int rc = require_test(h);
   if (rc) return rc;
   if (k < 1 || k > 1024) return fail(h, MR_ERR_BAD_ARG, "k must be in [1,1024], got %d", k);
@@ -1142,10 +1173,17 @@ int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) 
   h->out_k = k;
   if (model != MR_UBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   h->have_topk = false;
-  if ((rc = run_batches(h, model, bp, k, RUN_TOPK, nullptr))) return rc;
+  const bool streamed = ho && h->space == MR_SPACE_ITEM;          // the item-space pipeline copies slice by slice
+  rc = run_batches(h, model, bp, k, RUN_TOPK, streamed ? const_cast<TopkHostOut*>(ho) : nullptr);
+  if (streamed) { cudaError_t e = cudaStreamSynchronize(h->copy_stream); if (!rc && e != cudaSuccess) rc = fail(h, MR_ERR_CUDA, "result copy: %s", cudaGetErrorString(e)); }
+  if (rc) return rc;
   h->have_topk = true;
+  if (ho && !streamed) return mr_topk_fetch(h, k, ho->song, ho->score, ho->len);
+  if (ho) MR_CUDA(h, cudaStreamSynchronize(h->stream));
   return MR_OK;
 }
+
+int mr_topk_device(mr_handle* h, int model, double param, uint64_t seed, int k) { return topk_impl(h, model, param, seed, k, nullptr); }
 
 int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int32_t* out_len) {
   int rc = require_test(h);
@@ -1170,9 +1208,9 @@ int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** l
 }
 
 int mr_topk(mr_handle* h, int model, double param, uint64_t seed, int k, int32_t* out_song, double* out_score, int32_t* out_len) {
-  int rc = mr_topk_device(h, model, param, seed, k);
-  if (rc) return rc;
-  return mr_topk_fetch(h, k, out_song, out_score, out_len);
+  if (!out_song || !out_score || !out_len) return fail(h, MR_ERR_BAD_ARG, "null output");
+  const TopkHostOut ho{out_song, out_score, out_len};
+  return topk_impl(h, model, param, seed, k, &ho);
 }
 
 int mr_get_timing(mr_handle* h, double* ms_out, int n) {
