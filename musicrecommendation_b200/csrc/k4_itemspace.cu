@@ -125,13 +125,13 @@ template <> __device__ __forceinline__ RowWords<4> ld_row_words<4>(const void* p
 // A group's segments and entries (head row index, weight) are contiguous in the group-ordered arrays the host built; the CTA stages
 // them in shared memory with one coalesced round of loads, so the inner loop's only global accesses are the row loads themselves
 // (no dependent index -> row chain per round).
-template <bool kIbm, int W, int kRowsI = 2>
-__global__ void __launch_bounds__(256, (kIbm && kRowsI > 2) ? 5 : kHeadCtasPerSm)
+template <bool kIbm, int W>
+__global__ void __launch_bounds__(256, kHeadCtasPerSm)
 head_rowsum_kernel(const int4* __restrict__ grp_hdr, const int4* __restrict__ seg, const int* __restrict__ ge_row,
                    const uint32_t* __restrict__ ge_q, int seg_cap, int ent_cap, const uint16_t* __restrict__ g16,
                    const uint32_t* __restrict__ gq32, long long pitch, int n_songs, long long* __restrict__ sint, long long spitch) {
   constexpr int kVec = kIbm ? 2 * W : W;
-  constexpr int kRows = kIbm ? (W == 1 ? 4 : kRowsI) : (W == 4 ? 4 : 8);   // rows in flight per thread
+  constexpr int kRows = kIbm ? (W == 1 ? 4 : 2) : (W == 4 ? 4 : 8);   // rows in flight per thread
   extern __shared__ int4 s_dyn[];
   int4* s_seg = s_dyn;                                                // [seg_cap]
   uint32_t* s_row = reinterpret_cast<uint32_t*>(s_dyn + seg_cap);     // [ent_cap]
@@ -192,8 +192,6 @@ int launch_head_rowsum(int model, int words, int threads, const int4* grp_hdr, i
   if (smem > 48 * 1024) return -3;
 #define MR_HR(IBM, W) head_rowsum_kernel<IBM, W><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch)
   if (model == 1) { if (words == 4) MR_HR(false, 4); else if (words == 2) MR_HR(false, 2); else if (words == 1) MR_HR(false, 1); else return -2; }
-  else if (model == 2 && words == 4 && getenv("MRSCORE_IBM_ROWS4")) head_rowsum_kernel<true, 4, 4><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch);
-  else if (model == 2 && words == 2 && getenv("MRSCORE_IBM_ROWS4")) head_rowsum_kernel<true, 2, 8><<<grid, threads, smem, st>>>(grp_hdr, seg, ge_row, ge_q, seg_cap, ent_cap, g16, gq32, pitch, n_songs, sint, spitch);
   else if (model == 2) { if (words == 4) MR_HR(true, 4); else if (words == 2) MR_HR(true, 2); else if (words == 1) MR_HR(true, 1); else return -2; }
   else return -2;
 #undef MR_HR

@@ -42,7 +42,9 @@ struct mr_handle {
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
-  std::vector<uint32_t> h_qd;                  // per song q_26(d_s) (host copy: mr_set_test_users tags head entries with it)
+  struct SongInfo { int head; uint32_t v; };   // head row or -1; v = q_26(d_s) of a head song, train listeners of a tail song
+  std::vector<SongInfo> song_info;             // per song, 8 bytes: the one random access per test entry in mr_set_test_users
+  unsigned long long max_qsum = 0;             // max over songs of song_qsum
   std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
   bool ubm_int_ok = false;                     // every UBM numerator of the current shard is provably < 2^52 (top-k may rank the integers)
   int *d_item_song = nullptr, *d_item_len = nullptr; long long* d_item_begin = nullptr; uint8_t* d_item_split = nullptr; int n_items = 0;
@@ -722,7 +724,6 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<float> rsvf(T), rsdf(S);
   for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); }
   for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s], kQScaleIbm); rsd[s] = rs_of(deg_song_all[s], kQInvIbm); rsdf[s] = rsf_of(deg_song_all[s]); }
-  h->h_qd = qd;
   h->song_qsum.assign(S, 0);
   for (int s = 0; s < S; ++s)
     for (long long i = csc_ptr[s]; i < csc_ptr[s + 1]; ++i) h->song_qsum[s] += qv[csc_idx[i]];
@@ -794,6 +795,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if (const char* e = getenv("MRSCORE_HEAD_WORDS_I")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_i = w; }
   if (const char* e = getenv("MRSCORE_HEAD_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) h->head_threads = t; }
   h->n_groups = h->num_sms * std::min(32, kHeadCtasPerSm * 256 / h->head_threads);   // one wave of resident CTAs = one song tile for the whole batch
+  if (const char* e = getenv("MRSCORE_HEAD_GROUPS")) h->n_groups = std::max(1, atoi(e));   // test aid: few groups -> several users per group on small shards
   h->sel_pitch = (S + 63) / 64;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
@@ -814,6 +816,9 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
       head_song.push_back(s); lst_ptr.push_back(lst_ptr.back() + d);
     }
     h->n_head = static_cast<int>(head_song.size());
+    h->song_info.resize(S);
+    for (int s = 0; s < S; ++s) h->song_info[s] = {h->head_index[s], h->head_index[s] >= 0 ? qd[s] : static_cast<uint32_t>(h->deg_song_train[s])};
+    h->max_qsum = *std::max_element(h->song_qsum.begin(), h->song_qsum.end());
     if ((rc = dev_upload(h, &h->d_head_song, head_song.data(), head_song.size(), h->allocs))) return rc;
     if ((rc = dev_upload(h, &h->d_head_lst_ptr, lst_ptr.data(), lst_ptr.size(), h->allocs))) return rc;
   }
@@ -831,8 +836,17 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   if (rc) return rc;
   for (int u = 0; u < n_test; ++u)
     if (te_rowptr[u + 1] - te_rowptr[u] > 65535) return fail(h, MR_ERR_BAD_ARG, "test user %d has more than 65535 visible songs (u16 count panel)", u);
+  const bool dbg = getenv("MRSCORE_DEBUG_TIMING") != nullptr;
+  auto t_dbg = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mrscore] set_test_users: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_dbg).count());
+    t_dbg = now;
+  };
   MR_CUDA(h, cudaSetDevice(h->device));
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  lap("check_csr + sync");
   h->have_test = false; h->have_topk = false; h->out_k = 0;
   const int U = n_test; const long long nnz = te_rowptr[U];
   h->U = U; h->nnz_te = nnz;
@@ -844,15 +858,6 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   for (int u = 0; u < U; ++u) {
     rsa[u] = rs_of(deg_test[u], kQInvUbm); rsaf[u] = rsf_of(deg_test[u]);
     pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
-  }
-  {  // Sint_u[u][s] = sum_{j in I_u} Gq[j][s] <= sum_{j in I_u} song_qsum[j]
-    unsigned long long worst = 0;
-    for (int u = 0; u < U; ++u) {
-      unsigned long long sum = 0;
-      for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) sum += h->song_qsum[te_col[e]];
-      worst = std::max(worst, sum);
-    }
-    h->ubm_int_ok = worst < (1ULL << 52);
   }
   h->pair_index_base = pair_index_base;
   h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
@@ -874,6 +879,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
       h->max_batch_rows = std::max<int>(h->max_batch_rows, static_cast<int>(uni.size()));
     }
   }
+  lap("host arrays");
   if ((rc = slot_upload(h, mr_handle::SL_TE_PTR, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_TE_COL, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz)))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_TE_GROW, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz)))) return rc;
@@ -881,20 +887,38 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   if ((rc = slot_upload(h, mr_handle::SL_RSA_F, &h->d_rsa_f, rsaf.data(), rsaf.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_PAIR_BASE, &h->d_pair_base, pair_base.data(), pair_base.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_ROWS, &h->d_rows, rows_all.data(), rows_all.size()))) return rc;
+  lap("uploads 1");
   {  // item-space work lists: per user the precomputed head rows it sums, and its tail songs expanded on the fly
     std::vector<long long> hu_ptr(static_cast<size_t>(U) + 1, 0);
     std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q; std::vector<long long> tu_lptr(1, 0);
     h->h_tu_ptr.assign(static_cast<size_t>(U) + 1, 0);
     hu_row.reserve(static_cast<size_t>(nnz)); hu_song.reserve(static_cast<size_t>(nnz)); hu_q.reserve(static_cast<size_t>(nnz));
+    tu_user.reserve(static_cast<size_t>(nnz) / 2); tu_song.reserve(static_cast<size_t>(nnz) / 2); tu_lptr.reserve(static_cast<size_t>(nnz) / 2 + 1);
+    long long longest = 0;
     for (int u = 0; u < U; ++u) {
       for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) {
-        const int j = te_col[e]; const int hr = h->head_index[j];
-        if (hr >= 0) { hu_row.push_back(hr); hu_song.push_back(j); hu_q.push_back(h->h_qd[j]); }
-        else { tu_user.push_back(u); tu_song.push_back(j); tu_lptr.push_back(tu_lptr.back() + h->deg_song_train[j]); }
+        const int j = te_col[e];
+        const mr_handle::SongInfo si = h->song_info[j];
+        if (si.head >= 0) { hu_row.push_back(si.head); hu_song.push_back(j); hu_q.push_back(si.v); }
+        else { tu_user.push_back(u); tu_song.push_back(j); tu_lptr.push_back(tu_lptr.back() + si.v); }
       }
+      longest = std::max<long long>(longest, te_rowptr[u + 1] - te_rowptr[u]);
       hu_ptr[u + 1] = static_cast<long long>(hu_row.size());
       h->h_tu_ptr[u + 1] = static_cast<long long>(tu_user.size());
     }
+    // Sint_u[u][s] = sum_{j in I_u} Gq[j][s] <= sum_{j in I_u} qsum[j]: below 2^52 the top-k select may rank the UBM integers.  The cheap
+    // bound (longest row x largest qsum) decides almost always; otherwise the exact per-user sums do.
+    h->ubm_int_ok = static_cast<long double>(h->max_qsum) * static_cast<long double>(longest) < 4503599627370496.0L;
+    if (!h->ubm_int_ok) {
+      unsigned long long worst = 0;
+      for (int u = 0; u < U; ++u) {
+        unsigned long long bound = 0;
+        for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) bound += h->song_qsum[te_col[e]];
+        worst = std::max(worst, bound);
+      }
+      h->ubm_int_ok = worst < (1ULL << 52);
+    }
+    lap("item lists");
     if ((rc = slot_upload(h, mr_handle::SL_HU_PTR, &h->d_hu_ptr, hu_ptr.data(), hu_ptr.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_HU_ROW, &h->d_hu_row, hu_row.data(), hu_row.size()))) return rc;
     if ((rc = slot_upload(h, mr_handle::SL_HU_SONG, &h->d_hu_song, hu_song.data(), hu_song.size()))) return rc;
@@ -905,7 +929,9 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     h->h_tu_lptr = tu_lptr;
     h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
+    lap("uploads 2");
     if ((rc = plan_item_batches(h, hu_ptr, hu_row, hu_q))) return rc;
+    lap("plan_item_batches");
   }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_test = true;

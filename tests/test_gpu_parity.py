@@ -172,6 +172,29 @@ def test_item_space_balanced_groups_and_batches(oracle_lib, monkeypatch):
             assert_bits_equal(score, wv)
 
 
+def test_long_rows_with_grouped_head_pass(oracle_lib, monkeypatch):
+    """Rows longer than 65536 songs (sampled-cut top-k: integer select for UBM, fp32-bounded collect for IBM, fp64 for the blends) on a
+    shard whose head pass packs several users per work group and spans three batches."""
+    monkeypatch.setenv("MRSCORE_HEAD_GROUPS", "48")
+    monkeypatch.setenv("MRSCORE_ITEM_BATCH", "128")
+    ds = synth(T=3000, U=300, S=70000, seed=21)
+    want = {"ubm": oracle_lib.canon_scores(ds, oracle_lib.UBM), "ibm": oracle_lib.canon_scores(ds, oracle_lib.IBM)}
+    with MusicRecommender(ds, engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM) as mr:
+        info = mr.info()
+        assert info["batch_rows"] == 128 and info["head_groups"] == 48
+        for key, kind in KINDS.items():
+            song, score, ln = mr.getTopK(kind, k=500)
+            ws, wv, wl = oracle_lib.topk(want[key], 500)
+            np.testing.assert_array_equal(ln, wl)
+            np.testing.assert_array_equal(song, ws)
+            assert_bits_equal(score, wv)
+        for kind, okind, param, seed in ((_lib.MR_LC, oracle_lib.LC, 0.4, 0), (_lib.MR_AGG, oracle_lib.AGG, 0.5, 0), (_lib.MR_STOCH, oracle_lib.STOCH, 0.6, 9)):
+            song, score, ln = mr.getTopK(kind, k=500, param=param, seed=seed)
+            ws, wv, wl = oracle_lib.topk(oracle_lib.blend_dense(okind, param, want["ubm"], want["ibm"], seed), 500)
+            np.testing.assert_array_equal(song, ws)
+            assert_bits_equal(score, wv)
+
+
 def test_config_c1(engine, oracle_lib):
     ds = synth_config("c1")
     info = check_dataset(ds, oracle_lib, engine)
