@@ -398,7 +398,11 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
   int rc;
   const int U = h->U;
   h->batch_rows = kUserBatch;
-  if (h->space == MR_SPACE_ITEM) {
+  const size_t panel_rows_have = std::min(h->slot_cap[mr_handle::SL_SINT_U], h->slot_cap[mr_handle::SL_SINT_I]) / (static_cast<size_t>(h->spitch) * 8);
+  if (h->space == MR_SPACE_ITEM && static_cast<size_t>(U) <= panel_rows_have && (h->item_batch_cap <= 0 || U <= h->item_batch_cap) &&
+      h->slot_cap[mr_handle::SL_SEL] >= static_cast<size_t>(U) * h->sel_pitch * 8) {
+    h->batch_rows = std::max(kUserBatch, U);   // the panels of an earlier shard already hold this one as a single batch: no memory query
+  } else if (h->space == MR_SPACE_ITEM) {
     size_t free_b = 0, total_b = 0;
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
     const size_t per_row = static_cast<size_t>(h->spitch) * 16 + static_cast<size_t>(h->sel_pitch) * 8;
