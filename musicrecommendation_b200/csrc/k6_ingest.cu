@@ -28,6 +28,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -137,6 +138,22 @@ __global__ void parse_lines_kernel(const char* __restrict__ buf, long long file_
   s_hash[g] = hash_bytes(reinterpret_cast<const unsigned char*>(buf + t1 + 1), static_cast<int>(t2 - t1 - 1));
 }
 
+__global__ void line_flags_kernel(int* flag, long long n, long long first_label_line) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = i < first_label_line ? 1 : 2;
+}
+
+// first 8 bytes of a unique's string as a big-endian integer, zero padded: ordering by it never contradicts the byte order of the full
+// strings (ties are resolved on the host), so the device sorts the uniques and the host only orders the runs of equal prefixes
+__global__ void prefix_keys_kernel(const char* __restrict__ blob, const long long* __restrict__ str_off, int n_uniq, uint64_t* __restrict__ key) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_uniq) return;
+  const long long b = str_off[u], len = str_off[u + 1] - b;
+  uint64_t k = 0;
+  for (int i = 0; i < 8; ++i) k = (k << 8) | (i < len ? static_cast<unsigned char>(blob[b + i]) : 0u);
+  key[u] = k;
+}
+
 __global__ void iota_u32_kernel(uint32_t* p, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = static_cast<uint32_t>(i);
@@ -232,6 +249,8 @@ struct UniqueSet {            // result of step 3 for one id space
   std::vector<char> blob;     // representatives' strings, concatenated in unique-index order
   std::vector<long long> str_off;   // [n_uniq + 1]
   std::vector<int> flag;      // [n_uniq] OR of the elements' flags
+  std::vector<uint32_t> order;      // [n_uniq] unique indices sorted by the 8-byte string prefix (device radix sort)
+  std::vector<uint64_t> order_key;  // [n_uniq] the prefixes in that order
 };
 
 // elements = fields [off[e], off[e] + len[e]) of buf with hash[e], e in [0, n)
@@ -239,7 +258,7 @@ int unique_fields(mr_ingest* g, const char* d_buf, const uint64_t* d_hash, const
                   Temp& tmp, UniqueSet& out) {
   out.n_uniq = 0;
   ING_CUDA(out.elem_uniq.alloc(static_cast<size_t>(n)));
-  out.blob.clear(); out.str_off.assign(1, 0); out.flag.clear();
+  out.blob.clear(); out.str_off.assign(1, 0); out.flag.clear(); out.order.clear(); out.order_key.clear();
   if (n == 0) return MR_OK;
   DVec<uint64_t> key_sorted; DVec<uint32_t> idx, idx_sorted; DVec<int> head, incl, rep_elem, uniq_flag, collision;
   ING_CUDA(key_sorted.alloc(n)); ING_CUDA(idx.alloc(n)); ING_CUDA(idx_sorted.alloc(n)); ING_CUDA(head.alloc(n)); ING_CUDA(incl.alloc(n));
@@ -280,6 +299,18 @@ int unique_fields(mr_ingest* g, const char* d_buf, const uint64_t* d_hash, const
   if (total) ING_CUDA(cudaMemcpy(out.blob.data(), blob.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost));
   out.flag.resize(n_uniq);
   ING_CUDA(cudaMemcpy(out.flag.data(), uniq_flag.p, static_cast<size_t>(n_uniq) * sizeof(int), cudaMemcpyDeviceToHost));
+  {  // order of the uniques by string prefix
+    DVec<uint64_t> pk, pk_sorted; DVec<uint32_t> ui, ui_sorted;
+    ING_CUDA(pk.alloc(n_uniq)); ING_CUDA(pk_sorted.alloc(n_uniq)); ING_CUDA(ui.alloc(n_uniq)); ING_CUDA(ui_sorted.alloc(n_uniq));
+    prefix_keys_kernel<<<blocks_for(n_uniq), 256>>>(blob.p, str_off.p, n_uniq, pk.p);
+    iota_u32_kernel<<<blocks_for(n_uniq), 256>>>(ui.p, n_uniq);
+    ING_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk.p, pk_sorted.p, ui.p, ui_sorted.p, n_uniq));
+    ING_CUDA(tmp.reserve(need));
+    ING_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, need, pk.p, pk_sorted.p, ui.p, ui_sorted.p, n_uniq));
+    out.order.resize(n_uniq); out.order_key.resize(n_uniq);
+    ING_CUDA(cudaMemcpy(out.order.data(), ui_sorted.p, static_cast<size_t>(n_uniq) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    ING_CUDA(cudaMemcpy(out.order_key.data(), pk_sorted.p, static_cast<size_t>(n_uniq) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
   ING_CUDA(cudaGetLastError());
   return MR_OK;
 }
@@ -289,21 +320,28 @@ int unique_fields(mr_ingest* g, const char* d_buf, const uint64_t* d_hash, const
 int rank_uniques(const UniqueSet& u, int primary_bit, bool keep_rest, std::vector<int>& rank, std::vector<char>& chars, std::vector<int64_t>& off,
                  int* n_primary_out) {
   const int n = u.n_uniq;
-  std::vector<int> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  auto less = [&](int a, int b) {
-    const bool pa = (u.flag[a] & primary_bit) != 0, pb = (u.flag[b] & primary_bit) != 0;
-    if (pa != pb) return pa;
+  std::vector<uint32_t> sorted(u.order);                    // by 8-byte prefix (device); finish runs of equal prefixes with the full comparison
+  auto less = [&](uint32_t a, uint32_t b) {
     const long long la = u.str_off[a + 1] - u.str_off[a], lb = u.str_off[b + 1] - u.str_off[b];
     const int c = memcmp(u.blob.data() + u.str_off[a], u.blob.data() + u.str_off[b], static_cast<size_t>(std::min(la, lb)));
     return c != 0 ? c < 0 : la < lb;
   };
-  std::sort(order.begin(), order.end(), less);
+  for (int i = 0; i < n;) {
+    int j = i + 1;
+    while (j < n && u.order_key[j] == u.order_key[i]) ++j;
+    if (j - i > 1) std::sort(sorted.begin() + i, sorted.begin() + j, less);
+    i = j;
+  }
+  // primary uniques first (ids 0 .. n_primary-1), the others after them, each group in string order
+  std::vector<uint32_t> order; order.reserve(n);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < n; ++i)
+      if (((u.flag[sorted[i]] & primary_bit) != 0) == (pass == 0)) order.push_back(sorted[i]);
   rank.assign(n, -1);
   chars.clear(); off.assign(1, 0);
   int n_primary = 0;
   for (int i = 0; i < n; ++i) {
-    const int x = order[i];
+    const int x = static_cast<int>(order[i]);
     const bool primary = (u.flag[x] & primary_bit) != 0;
     if (primary) ++n_primary;
     if (!primary && !keep_rest) continue;
@@ -372,6 +410,14 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
   const uint64_t total_bytes = lens[0] + lens[1] + lens[2];
   if (total_bytes >= (1ULL << 40)) return ing_fail(g, MR_ERR_BAD_ARG, "input too large");
   Temp tmp;
+  const bool dbg = getenv("MRSCORE_DEBUG_TIMING") != nullptr;
+  auto t_lap = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[mrscore] ingest: %s %.1f ms\n", what, ms_since(t_lap));
+    t_lap = std::chrono::steady_clock::now();
+  };
   // ---- 0: the three files back to back in one device buffer
   auto t0 = std::chrono::steady_clock::now();
   DVec<char> buf;
@@ -380,6 +426,7 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
   for (int f = 0; f < 3; ++f)
     if (lens[f]) ING_CUDA(cudaMemcpy(buf.p + fbeg[f], bufs[f], static_cast<size_t>(lens[f]), cudaMemcpyHostToDevice));
   g->timing[0] = ms_since(t0);
+  lap("alloc + h2d");
   // ---- 1: newline positions per file
   t0 = std::chrono::steady_clock::now();
   DVec<long long> nl[3]; DVec<long long> n_sel;
@@ -413,6 +460,7 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
     ING_CUDA(cudaMemcpy(&last, buf.p + fbeg[f + 1] - 1, 1, cudaMemcpyDeviceToHost));
     n_lines[f] = done + (last != '\n' ? 1 : 0);
   }
+  lap("newline count + select");
   for (int f = 0; f < 3; ++f) line0[f + 1] = line0[f] + n_lines[f];
   const long long L = line0[3];
   if (L >= (1LL << 31)) return ing_fail(g, MR_ERR_BAD_ARG, "more than 2^31 lines");
@@ -421,6 +469,7 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
   ING_CUDA(u_off.alloc(L)); ING_CUDA(s_off.alloc(L)); ING_CUDA(u_len.alloc(L)); ING_CUDA(s_len.alloc(L)); ING_CUDA(u_hash.alloc(L)); ING_CUDA(s_hash.alloc(L));
   ING_CUDA(first_bad.alloc(1));
   ING_CUDA(cudaMemset(first_bad.p, 0xff, sizeof(unsigned long long)));
+  lap("per-line arrays alloc");
   for (int f = 0; f < 3; ++f)
     if (n_lines[f])
       parse_lines_kernel<<<blocks_for(n_lines[f]), 256>>>(buf.p, fbeg[f], fbeg[f + 1], nl[f].p, n_nl[f], n_lines[f], line0[f], u_off.p, u_len.p, s_off.p,
@@ -433,13 +482,13 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
     return ing_fail(g, MR_ERR_BAD_ARG, "scala.MatchError: line %lld of the %s file does not have 3 tab-separated fields", static_cast<long long>(bad) - line0[f] + 1,
                     kFileName[f]);
   }
+  lap("parse");
   g->timing[1] = ms_since(t0);
   // per-element flags: users 1 = train / test line, 2 = label line; songs 1 = train or test line, 2 = label line
-  std::vector<int> h_flag(static_cast<size_t>(L));
-  for (long long i = 0; i < L; ++i) h_flag[i] = i < line0[2] ? 1 : 2;
   DVec<int> flag;
   ING_CUDA(flag.alloc(L));
-  if (L) ING_CUDA(cudaMemcpy(flag.p, h_flag.data(), static_cast<size_t>(L) * sizeof(int), cudaMemcpyHostToDevice));
+  if (L) line_flags_kernel<<<blocks_for(L), 256>>>(flag.p, L, line0[2]);
+  lap("flags");
   // ---- 3/4: id spaces
   t0 = std::chrono::steady_clock::now();
   DVec<int> user_id, song_id;
