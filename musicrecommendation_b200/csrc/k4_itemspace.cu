@@ -7,7 +7,8 @@
 // Popular ("head") songs are shared by many test users, so their rows G[j][:], Gq[j][:] are computed once per train set
 // (gram_head_* below, or the tcgen05 count GEMM for dense-friendly shapes) and kept in HBM as dense rows of 6 bytes per entry
 // (u16 count + u32 weighted sum, overflowing entries in an exact exception list); a test user's score
-// row is then a sum of |I_u ∩ head| coalesced, streaming row reads (head_rowsum_kernel — HBM-bandwidth bound).  The long tail
+// row is then a sum of |I_u ∩ head| coalesced row reads (head_rowsum_kernel — each distinct row crosses HBM once per batch, the rest is
+// served from L2; bound by the L2 -> SM fabric).  The long tail
 // of rarely heard songs is expanded on the fly through the inverted index with exact 64-bit integer atomics
 // (tail_scatter_kernel).  Every entry is an exact integer, so the result equals the user-space engine and the oracle bit for bit.
 #include "mr_common.cuh"

@@ -3,10 +3,12 @@
 // HBM layout:
 //   train CSR  (user -> songs)   tr_ptr i64[T+1], tr_col i32[nnz]        MusicRecommender.scala:55  trainUsersToSongsMap
 //   train CSC  (song -> users)   csc_ptr i64[S+1], csc_idx i32[nnz]      MusicRecommender.scala:60  songsToUsersMap (train part)
-//   qv u32[T], qd u32[S]         rint(2^31 / sqrt(deg))                   cosine denominators MR:147 / MR:237 in fixed point
-//   rsa f64[U], rsd f64[S]       2^-31 / sqrt(deg)                        the other half of each denominator
+//   qv u32[T], qd u32[S]         rint(2^24 / sqrt(deg)), rint(2^26 / sqrt(deg))   cosine denominators MR:147 / MR:237 in fixed point
+//   rsa f64[U], rsd f64[S]       2^-24 / sqrt(deg), 2^-26 / sqrt(deg)              the other half of each denominator
 //   A_tr  u8[T][pitchS], A_trT u8[S][pitchT]   dense 0/1 operands of the tensor-core count GEMM (tensor engine only)
-//   per batch of 128 test users: Ct u16[T][128], Sint_u / Sint_i i64[128][spitch], G i32[rows][ldg], select bits
+//   user space, per batch of 128 test users: Ct u16[T][128], Sint_u / Sint_i i64[128][spitch], G i32[rows][ldg], select bits
+//   item space: head rows G16 / Gq32 (once per train set), Sint_u / Sint_i i64[batch][spitch] with batch = as many test users as fit
+//   (plan_item_batches), balanced work groups of the head pass, per-slice tail scatter -> mask -> top-k -> streamed copy of the result
 #include "../../include/mrscore.h"
 #include "mr_common.cuh"
 #include "mr_kernels.h"
