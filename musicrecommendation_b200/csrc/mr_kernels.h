@@ -64,8 +64,8 @@ struct HeadExceptions {      // entries of the packed head rows whose count exce
 };
 int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
                              const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
-                             long long pitch, int num_sms, cudaStream_t st);
-int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int r0, int n_rows, long long pitch, uint16_t* g16,
+                             long long pitch, int packed, int num_sms, cudaStream_t st);
+int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, uint16_t* g16,
                           uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
 // model: 1 = UBM pass over Gq32, 2 = IBM pass over G16; words = 32-bit words per row load (1, 2 or 4); threads per CTA (a CTA covers
 // threads * songs-per-thread songs); groups / segments: see k4_itemspace.cu

@@ -293,19 +293,22 @@ int ensure_head_rows(mr_handle* h) {
   // staging chunk.  Tensor engine: <= 8 GiB of (u32 + u64) rows, a multiple of the 128-row GEMM tile.  Scatter path: small enough
   // (<= 64 MiB) that the rows being built stay L2-resident, so the 6e9 integer atomics of an MSD-sized precompute are resolved in
   // L2 instead of as DRAM read-modify-writes (measured: 260 GB of DRAM traffic for the first 2048-row chunk otherwise).
-  long long chunk;
+  long long chunk; bool packed = false;
   if (tensor) {
     chunk = (8LL << 30) / (h->spitch * 12) / 128 * 128;
     chunk = std::max<long long>(128, std::min<long long>(chunk, 4096));
   } else {
-    chunk = std::max<long long>(4, std::min<long long>((64LL << 20) / (h->spitch * 12), 4096));
+    // one packed 64-bit accumulator per entry when no weighted sum can reach 2^44 and no count 2^20 (any realistic data set)
+    packed = h->max_qsum < (1ULL << 44) && *std::max_element(h->deg_song_train.begin(), h->deg_song_train.end()) < (1 << 20) &&
+             !getenv("MRSCORE_PRECOMPUTE_UNPACKED");
+    chunk = std::max<long long>(4, std::min<long long>((64LL << 20) / (h->spitch * (packed ? 8 : 12)), 4096));
     if (const char* e = getenv("MRSCORE_PRECOMPUTE_CHUNK")) chunk = std::max(1LL, atoll(e));
   }
   std::vector<void*> tmp;
   uint32_t* g_stage = nullptr; unsigned long long* gq_stage = nullptr;
   HeadExceptions ex{};
   ex.capacity = 1u << 24;
-  if ((rc = dev_alloc(h, &g_stage, static_cast<size_t>(chunk) * h->spitch, tmp)) ||
+  if ((rc = dev_alloc(h, &g_stage, packed ? 1 : static_cast<size_t>(chunk) * h->spitch, tmp)) ||
       (rc = dev_alloc(h, &gq_stage, static_cast<size_t>(chunk) * h->spitch, tmp)) ||
       (rc = dev_alloc(h, &ex.count, 1, tmp)) || (rc = dev_alloc(h, &ex.row, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.song, ex.capacity, tmp)) ||
       (rc = dev_alloc(h, &ex.g_extra, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.gq_extra, ex.capacity, tmp))) { free_list(tmp); return rc; }
@@ -350,12 +353,12 @@ int ensure_head_rows(mr_handle* h) {
     } else {
       PhaseTimer t(h, MR_T_PRECOMPUTE);
       int lrc = launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                         h->d_qv, g_stage, gq_stage, h->spitch, h->num_sms, h->stream);
+                                         h->d_qv, g_stage, gq_stage, h->spitch, packed ? 1 : 0, h->num_sms, h->stream);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_scatter failed"));
     }
     PhaseTimer t(h, MR_T_PRECOMPUTE);
-    int lrc = launch_pack_head_rows(g_stage, gq_stage, r0, nr, h->spitch, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
+    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
     h->launches++;
     if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_pack_head_rows failed"));
   }

@@ -155,6 +155,8 @@ def test_item_space_balanced_groups_and_batches(oracle_lib, monkeypatch):
             monkeypatch.setenv("MRSCORE_ITEM_BATCH", cap)
         monkeypatch.setenv("MRSCORE_HEAD_WORDS_U", words)
         monkeypatch.setenv("MRSCORE_HEAD_WORDS_I", words)
+        if words == "1":   # the two-atomics fallback of the head-row precompute (data sets whose sums could overflow the packed accumulator)
+            monkeypatch.setenv("MRSCORE_PRECOMPUTE_UNPACKED", "1")
         with MusicRecommender(ds, engine=_lib.MR_ENGINE_SPARSE, space=_lib.MR_SPACE_ITEM) as mr:
             info = mr.info()
             assert info["batch_rows"] == (ds.U if not cap else max(128, -(-ds.U // -(-ds.U // int(cap)))))
