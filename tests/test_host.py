@@ -104,3 +104,14 @@ def test_native_ingest_has_no_cpu_fallback(mrlib):
     with pytest.raises(_lib.MrError) as ei:
         recommender.dataset_from_streams_native(b"A\ts1\t1\n", b"X\ts1\t1\n", b"X\ts2\t1\n")
     assert ei.value.code == _lib.MR_ERR_CUDA and "no CPU fallback" in ei.value.msg
+
+
+def test_ingest_selectors_match_the_header():
+    """The MR_ING_* selectors of mr_ingest_get are positional: the Python constants must follow the header's enum order."""
+    header = (ROOT / "include" / "mrscore.h").read_text()
+    body = header[header.index("enum { MR_ING_TR_PTR"):]
+    body = body[:body.index("};")]
+    names = re.findall(r"\bMR_ING_[A-Z_]+", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert len(names) == 16 and len(set(names)) == 16
+    for i, name in enumerate(names):
+        assert getattr(_lib, name) == i, name
