@@ -80,6 +80,15 @@ int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, cons
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
                         const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs, cudaStream_t st);
 
+// ---- per-shard work lists of the item-space engine, built on the device (k7_testlists.cu)
+size_t test_lists_temp_bytes(long long nnz);
+int launch_build_test_lists(const long long* te_ptr, const int* te_col, int n_users, long long nnz, const int2* song_info, int* flag,
+                            int* head_pos, long long* deg, long long* lsum, void* cub_tmp, size_t cub_tmp_bytes, int* hu_row, int* hu_song,
+                            uint32_t* hu_q, long long* hu_ptr, int* tu_user, int* tu_song, long long* tu_lptr, long long* tu_ptr,
+                            cudaStream_t st);
+int launch_gather_group_entries(const int4* desc, int n_desc, const int* hu_row, const uint32_t* hu_q, int* ge_row, uint32_t* ge_q,
+                                cudaStream_t st);
+
 // ---- K3 (k3_topk.cu)
 int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
                          long long spitch, cudaStream_t st);

@@ -45,6 +45,7 @@ struct mr_handle {
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
   struct SongInfo { int head; uint32_t v; };   // head row or -1; v = q_26(d_s) of a head song, train listeners of a tail song
+  int2* d_song_info = nullptr;                 // the same records on the device (k7_testlists.cu)
   std::vector<SongInfo> song_info;             // per song, 8 bytes: the one random access per test entry in mr_set_test_users
   unsigned long long max_qsum = 0;             // max over songs of song_qsum
   std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
@@ -68,7 +69,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -399,7 +400,7 @@ int ensure_head_rows(mr_handle* h) {
 // panels (two models, 8 bytes per (user, song)) fit in HBM next to the head rows — a large batch shares the row tiles of popular
 // songs among more users (head_rowsum_kernel) — split evenly, plus per batch the balanced work groups of head_rowsum_kernel:
 // segments (Sint row, head-entry range) packed longest-first into n_groups bins of equal total length.
-int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const std::vector<int>& hu_row, const std::vector<uint32_t>& hu_q) {
+int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
   int rc;
   const int U = h->U;
   h->batch_rows = kUserBatch;
@@ -428,8 +429,8 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
 
   const int G = h->n_groups, B = h->batch_rows;
   const int n_batches = (U + B - 1) / B;
-  std::vector<int4> seg, grp_hdr; std::vector<int> ge_row, split_rows; std::vector<uint32_t> ge_q;
-  ge_row.reserve(hu_row.size()); ge_q.reserve(hu_q.size());
+  std::vector<int4> seg, grp_hdr, copy_desc; std::vector<int> split_rows;
+  long long ge_size = 0;   // entries of the group-ordered copies (segments padded to multiples of 4)
   h->h_split_ptr.assign(1, 0);
   h->seg_cap = 1; h->ent_cap = 1;
   struct Item { int row, e0, e1, acc; };
@@ -460,24 +461,29 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr, const 
       heap.push({top.first + (items[i].e1 - items[i].e0) + kRowCost, top.second});
     }
     for (int g = 0; g < G; ++g) {   // the group's segments and entries, contiguous: the CTA stages them in shared memory
-      const int seg0 = static_cast<int>(seg.size()), ent0 = static_cast<int>(ge_row.size());
+      const int seg0 = static_cast<int>(seg.size());
+      const long long ent0 = ge_size;
       for (int i : bins[g]) {
-        const int local = static_cast<int>(ge_row.size()) - ent0, n = items[i].e1 - items[i].e0;
+        const int local = static_cast<int>(ge_size - ent0), n = items[i].e1 - items[i].e0;
         seg.push_back(make_int4(items[i].row, local, local + n, items[i].acc));
-        ge_row.insert(ge_row.end(), hu_row.begin() + items[i].e0, hu_row.begin() + items[i].e1);
-        ge_q.insert(ge_q.end(), hu_q.begin() + items[i].e0, hu_q.begin() + items[i].e1);
+        if (n > 0) copy_desc.push_back(make_int4(items[i].e0, static_cast<int>(ge_size), n, 0));   // gathered on the device
+        ge_size += n;
       }
-      const int n_seg = static_cast<int>(seg.size()) - seg0, n_ent = static_cast<int>(ge_row.size()) - ent0;
-      grp_hdr.push_back(make_int4(seg0, n_seg, ent0, n_ent));
+      const int n_seg = static_cast<int>(seg.size()) - seg0, n_ent = static_cast<int>(ge_size - ent0);
+      grp_hdr.push_back(make_int4(seg0, n_seg, static_cast<int>(ent0), n_ent));
       h->seg_cap = std::max(h->seg_cap, n_seg); h->ent_cap = std::max(h->ent_cap, n_ent);
     }
   }
+  if (ge_size >= (1LL << 31)) return fail(h, MR_ERR_BAD_ARG, "too many head entries in one shard");
   if (static_cast<size_t>(h->seg_cap) * 16 + static_cast<size_t>(h->ent_cap) * 8 > 48 * 1024)
     return fail(h, MR_ERR_BAD_ARG, "head_rowsum work group too large for shared-memory staging (%d segments, %d entries)", h->seg_cap, h->ent_cap);
   if ((rc = slot_upload(h, mr_handle::SL_SEG, &h->d_seg, seg.data(), seg.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_GRP_HDR, &h->d_grp_hdr, grp_hdr.data(), grp_hdr.size()))) return rc;
-  if ((rc = slot_upload(h, mr_handle::SL_GE_ROW, &h->d_ge_row, ge_row.data(), ge_row.size()))) return rc;
-  if ((rc = slot_upload(h, mr_handle::SL_GE_Q, &h->d_ge_q, ge_q.data(), ge_q.size()))) return rc;
+  int4* d_desc = nullptr;
+  if ((rc = slot_upload(h, mr_handle::SL_COPY_DESC, &d_desc, copy_desc.data(), copy_desc.size()))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_GE_ROW, &h->d_ge_row, static_cast<size_t>(ge_size)))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_GE_Q, &h->d_ge_q, static_cast<size_t>(ge_size)))) return rc;
+  MR_LAUNCH(h, launch_gather_group_entries(d_desc, static_cast<int>(copy_desc.size()), h->d_hu_row, h->d_hu_q, h->d_ge_row, h->d_ge_q, h->stream));
   if ((rc = slot_upload(h, mr_handle::SL_SPLIT_ROWS, &h->d_split_rows, split_rows.data(), split_rows.size()))) return rc;
   MR_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging vectors above are pageable and go out of scope
   return MR_OK;
@@ -828,6 +834,8 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     h->song_info.resize(S);
     for (int s = 0; s < S; ++s) h->song_info[s] = {h->head_index[s], h->head_index[s] >= 0 ? qd[s] : static_cast<uint32_t>(h->deg_song_train[s])};
     h->max_qsum = *std::max_element(h->song_qsum.begin(), h->song_qsum.end());
+    static_assert(sizeof(mr_handle::SongInfo) == sizeof(int2), "SongInfo is uploaded as int2");
+    if ((rc = dev_upload(h, &h->d_song_info, reinterpret_cast<const int2*>(h->song_info.data()), h->song_info.size(), h->allocs))) return rc;
     if ((rc = dev_upload(h, &h->d_head_song, head_song.data(), head_song.size(), h->allocs))) return rc;
     if ((rc = dev_upload(h, &h->d_head_lst_ptr, lst_ptr.data(), lst_ptr.size(), h->allocs))) return rc;
   }
@@ -897,24 +905,26 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   if ((rc = slot_upload(h, mr_handle::SL_PAIR_BASE, &h->d_pair_base, pair_base.data(), pair_base.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_ROWS, &h->d_rows, rows_all.data(), rows_all.size()))) return rc;
   lap("uploads 1");
-  {  // item-space work lists: per user the precomputed head rows it sums, and its tail songs expanded on the fly
+  {  // item-space work lists (k7_testlists.cu): per user the precomputed head rows it sums, and its tail songs expanded on the fly
     std::vector<long long> hu_ptr(static_cast<size_t>(U) + 1, 0);
-    std::vector<int> hu_row, hu_song, tu_user, tu_song; std::vector<uint32_t> hu_q; std::vector<long long> tu_lptr(1, 0);
     h->h_tu_ptr.assign(static_cast<size_t>(U) + 1, 0);
-    hu_row.reserve(static_cast<size_t>(nnz)); hu_song.reserve(static_cast<size_t>(nnz)); hu_q.reserve(static_cast<size_t>(nnz));
-    tu_user.reserve(static_cast<size_t>(nnz) / 2); tu_song.reserve(static_cast<size_t>(nnz) / 2); tu_lptr.reserve(static_cast<size_t>(nnz) / 2 + 1);
-    long long longest = 0;
-    for (int u = 0; u < U; ++u) {
-      for (long long e = te_rowptr[u]; e < te_rowptr[u + 1]; ++e) {
-        const int j = te_col[e];
-        const mr_handle::SongInfo si = h->song_info[j];
-        if (si.head >= 0) { hu_row.push_back(si.head); hu_song.push_back(j); hu_q.push_back(si.v); }
-        else { tu_user.push_back(u); tu_song.push_back(j); tu_lptr.push_back(tu_lptr.back() + si.v); }
-      }
-      longest = std::max<long long>(longest, te_rowptr[u + 1] - te_rowptr[u]);
-      hu_ptr[u + 1] = static_cast<long long>(hu_row.size());
-      h->h_tu_ptr[u + 1] = static_cast<long long>(tu_user.size());
-    }
+    const size_t n1 = static_cast<size_t>(nnz) + 1;
+    int *d_flag = nullptr, *d_head_pos = nullptr; long long *d_deg = nullptr, *d_lsum = nullptr, *d_tu_ptr = nullptr; char* d_tmp = nullptr;
+    const size_t tmp_bytes = test_lists_temp_bytes(nnz);
+    if ((rc = slot_alloc(h, mr_handle::SL_L_FLAG, &d_flag, n1)) || (rc = slot_alloc(h, mr_handle::SL_L_HEADPOS, &d_head_pos, n1)) ||
+        (rc = slot_alloc(h, mr_handle::SL_L_DEG, &d_deg, n1)) || (rc = slot_alloc(h, mr_handle::SL_L_LSUM, &d_lsum, n1)) ||
+        (rc = slot_alloc(h, mr_handle::SL_L_TMP, &d_tmp, tmp_bytes)) || (rc = slot_alloc(h, mr_handle::SL_TU_PTR, &d_tu_ptr, hu_ptr.size())) ||
+        (rc = slot_alloc(h, mr_handle::SL_HU_PTR, &h->d_hu_ptr, hu_ptr.size())) || (rc = slot_alloc(h, mr_handle::SL_HU_ROW, &h->d_hu_row, n1)) ||
+        (rc = slot_alloc(h, mr_handle::SL_HU_SONG, &h->d_hu_song, n1)) || (rc = slot_alloc(h, mr_handle::SL_HU_Q, &h->d_hu_q, n1)) ||
+        (rc = slot_alloc(h, mr_handle::SL_TU_USER, &h->d_tu_user, n1)) || (rc = slot_alloc(h, mr_handle::SL_TU_SONG, &h->d_tu_song, n1)) ||
+        (rc = slot_alloc(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, n1)))
+      return rc;
+    MR_LAUNCH(h, launch_build_test_lists(h->d_te_ptr, h->d_te_col, U, nnz, h->d_song_info, d_flag, d_head_pos, d_deg, d_lsum, d_tmp, tmp_bytes, h->d_hu_row,
+                                         h->d_hu_song, h->d_hu_q, h->d_hu_ptr, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, d_tu_ptr, h->stream));
+    MR_CUDA(h, cudaMemcpyAsync(hu_ptr.data(), h->d_hu_ptr, hu_ptr.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    MR_CUDA(h, cudaMemcpyAsync(h->h_tu_ptr.data(), d_tu_ptr, h->h_tu_ptr.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    long long longest = 0;   // overlaps the device work
+    for (int u = 0; u < U; ++u) longest = std::max<long long>(longest, te_rowptr[u + 1] - te_rowptr[u]);
     // Sint_u[u][s] = sum_{j in I_u} Gq[j][s] <= sum_{j in I_u} qsum[j]: below 2^52 the top-k select may rank the UBM integers.  The cheap
     // bound (longest row x largest qsum) decides almost always; otherwise the exact per-user sums do.
     h->ubm_int_ok = static_cast<long double>(h->max_qsum) * static_cast<long double>(longest) < 4503599627370496.0L;
@@ -927,19 +937,13 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
       }
       h->ubm_int_ok = worst < (1ULL << 52);
     }
-    lap("item lists");
-    if ((rc = slot_upload(h, mr_handle::SL_HU_PTR, &h->d_hu_ptr, hu_ptr.data(), hu_ptr.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_HU_ROW, &h->d_hu_row, hu_row.data(), hu_row.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_HU_SONG, &h->d_hu_song, hu_song.data(), hu_song.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_HU_Q, &h->d_hu_q, hu_q.data(), hu_q.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_TU_USER, &h->d_tu_user, tu_user.data(), tu_user.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_TU_SONG, &h->d_tu_song, tu_song.data(), tu_song.size()))) return rc;
-    if ((rc = slot_upload(h, mr_handle::SL_TU_LPTR, &h->d_tu_lptr, tu_lptr.data(), tu_lptr.size()))) return rc;
-    h->h_tu_lptr = tu_lptr;
-    h->n_head_entries = static_cast<long long>(hu_row.size()); h->n_tail_entries = static_cast<long long>(tu_user.size());
+    MR_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_head_entries = hu_ptr[U]; h->n_tail_entries = h->h_tu_ptr[U];
+    h->h_tu_lptr.resize(static_cast<size_t>(h->n_tail_entries) + 1);
+    MR_CUDA(h, cudaMemcpyAsync(h->h_tu_lptr.data(), h->d_tu_lptr, h->h_tu_lptr.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    lap("device work lists");
     h->space = h->space_flag == MR_SPACE_AUTO ? (U >= 1024 ? MR_SPACE_ITEM : MR_SPACE_USER) : h->space_flag;
-    lap("uploads 2");
-    if ((rc = plan_item_batches(h, hu_ptr, hu_row, hu_q))) return rc;
+    if ((rc = plan_item_batches(h, hu_ptr))) return rc;
     lap("plan_item_batches");
   }
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
