@@ -23,6 +23,7 @@
 
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <chrono>
@@ -445,7 +446,7 @@ int ingest_impl(mr_ingest* g, int device, const char* const bufs[3], const uint6
     long long done = 0;
     for (long long p0 = fbeg[f]; p0 < fbeg[f + 1]; p0 += piece) {
       const int cnt = static_cast<int>(std::min<long long>(piece, fbeg[f + 1] - p0));
-      cub::CountingInputIterator<long long> it(p0);
+      thrust::counting_iterator<long long> it(p0);
       size_t need = 0;
       ING_CUDA(cub::DeviceSelect::If(nullptr, need, it, nl[f].p + done, n_sel.p, cnt, IsNewline{buf.p}));
       ING_CUDA(tmp.reserve(need));
