@@ -115,3 +115,20 @@ def test_ingest_selectors_match_the_header():
     assert len(names) == 16 and len(set(names)) == 16
     for i, name in enumerate(names):
         assert getattr(_lib, name) == i, name
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(mrlib, tmp_path):
+    """include/mrscore.h must be consumable from C99 (JNI / JNA / Panama bind a C ABI): compile and link examples/c_abi_demo.c with gcc
+    against the built library and run it; without a GPU it must stop at mr_create with MR_ERR_CUDA."""
+    import subprocess
+    import torch
+    exe = tmp_path / "c_abi_demo"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(ROOT / "examples" / "c_abi_demo.c"),
+                    "-L", str(ROOT / "musicrecommendation_b200"), "-lmrscore", "-Wl,-rpath," + str(ROOT / "musicrecommendation_b200"), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+        assert "user 0  #1" in r.stdout
+    else:
+        assert r.returncode == _lib.MR_ERR_CUDA and "no CPU fallback" in r.stderr
