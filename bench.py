@@ -1,23 +1,27 @@
 #!/usr/bin/env python
 """bench.py — scored (test-user, song) pairs / second for UBM + IBM scoring with top-500 ranking (BASELINE.json metric).
 
-A "step" scores every (test user, song) pair of this rank's test-user shard once with the user-based model and once with
-the item-based model and ranks the top 500 per user for each: 2 * (U*S - nnz_test) scored pairs per rank.
+  python bench.py --gpus N --steps K --warmup W [--workload msd|c1|c2|c3|ksplit] [--impl reference]
 
-  python bench.py --gpus N --steps K --warmup W [--workload msd|c3|c2|c1] [--impl reference]
+Workload `msd` (default) is BASELINE.json configs[3], the whole job: the MSD-shaped synthetic data set (909 318 train users, 384 546
+songs, ~42 M train triplets) and ALL 110 000 test users, sharded by test user over the N GPUs (distributed.scala:450-452), train
+replica on every GPU.  STRONG scaling: the work is fixed, N GPUs split it.  One step = what getUserBasedModel + getItemBasedModel
+(+ the new top-500) do for the whole test set, with nothing amortised across steps:
 
-Workload `msd` (default) is BASELINE.json configs[3]: the MSD-shaped synthetic data set (909 318 train users, 384 546 songs,
-~42 M train triplets, 110 000 test users), train replica on every GPU, test users sharded 13 750 per GPU (weak scaling: N GPUs
-score N * 13 750 users; N = 8 is the full configuration).  No data-path collective: shards are independent
-(distributed.scala:450-452); the only exchange would be the final top-k gather, which is outside the timed region.
+    head-row precompute (the only place the item-item intersection counts |U_i ∩ U_j| are computed at this scale; the reference's
+    model builders have no reusable half, MR:132-170, 222-261)  ->  per batch of test users: head pass, tail scatter, top-500 select,
+    for UBM and for IBM            = 2 * (110 000 * S - nnz_test) scored pairs per step.
 
 One JSON line on rank 0:
-  value      whole-job pairs/s with the CSR already resident in HBM (mr_topk_device only), CUDA-event timed, max over ranks
-  e2e        the same through the host-buffer C-ABI calls: mr_set_test_users (pinned host -> device) + mr_topk (device -> host)
-  roofline   dominant kernel (by CUDA-event share): algorithmic bytes per launch / average launch time vs measured HBM peak
+  value         whole-job pairs/s, test CSR already resident in HBM, CUDA events on the library stream, max over ranks
+  e2e           the same through the host-buffer C-ABI: mr_set_test_users (pinned host -> device) + mr_topk (device -> host) and, for N > 1,
+                the NCCL gather of the packed top-k blocks to rank 0 (the reference's `.collect`, DIST:451)
+  steady_state  the per-step figure WITHOUT the precompute (a service that keeps the train set's head rows): secondary
+  roofline      dominant kernel (by CUDA-event share): algorithmic bytes per launch / average launch time vs the measured HBM peak
   cpu_baseline  the oracle's canonical CPU port (OpenMP, all host threads) on a bounded sample of the same test users
-`--impl reference` times that CPU port alone (the Scala reference cannot run here: no JVM; the as-written loops are
-infeasible beyond configs[0]/[1] — SURVEY.md §8d) and prints the same line with "impl": "reference".
+`--impl reference` times that CPU port alone (the Scala reference cannot run here: no JVM; its loops as written are infeasible beyond
+configs[0]/[1] — SURVEY.md §8d) on rank 0 with every host thread the process may use and prints the same line with "impl": "reference".
+`--workload c1|c2` add the as-written sequential and `.par` CPU legs; `--workload ksplit` is BASELINE configs[4] (K-split item-item sweep).
 """
 from __future__ import annotations
 
@@ -36,7 +40,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 K_TOP = 500
-USERS_PER_GPU = 13750
+N_TEST_USERS = 110000          # BASELINE configs[3]
+METRIC = "scored (test-user, song) pairs/sec, UBM+IBM with top-500"
 
 
 def log(*a):
@@ -55,22 +60,33 @@ def emit(line: dict):
     _REAL_STDOUT.flush()
 
 
-def make_workload(name: str, rank: int, world: int):
+def host_threads() -> int:
+    """Threads this process may run on (torchrun exports OMP_NUM_THREADS=1; the CPU legs set their thread count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def make_workload(name: str, rank: int, world: int, users_total: int = 0):
     from musicrecommendation_b200.dataset import synth_config
+    from musicrecommendation_b200.distributed import shard_range
     t0 = time.time()
     if name == "msd":
         full = synth_config("c4")
-        u0, u1 = rank * USERS_PER_GPU, (rank + 1) * USERS_PER_GPU
+        n_users = min(users_total or N_TEST_USERS, full.U)
+        u0, u1 = shard_range(n_users, rank, world)
         ds = full.shard_test_users(u0, u1)
-        desc = (f"BASELINE configs[3]: MSD-shaped synthetic, T={full.T} train users, S={full.S} songs, nnz_train={full.nnz_tr}, "
-                f"{USERS_PER_GPU} test users per GPU (of 110000), train replica per GPU")
+        desc = (f"BASELINE configs[3]: MSD-shaped synthetic, T={full.T} train users, S={full.S} songs, nnz_train={full.nnz_tr}, all {n_users} test users "
+                f"sharded by test user over {world} GPU(s), train replica per GPU; head-row precompute inside every step")
+        total_pairs = 2 * (n_users * full.S - int(full.te_ptr[n_users]))
     else:
         full = synth_config(name)
-        # weak scaling on the small shapes: every rank scores the same U test users (replicas), no sharding possible below U
-        ds = full
-        desc = f"BASELINE {name}: T={full.T}, U={full.U} per GPU, S={full.S}"
+        ds = full            # the small shapes do not shard (U = 10..100): every rank scores the same users (replicas)
+        desc = f"BASELINE {name}: T={full.T}, U={full.U}, S={full.S}" + (f" (replicated on {world} GPUs)" if world > 1 else "")
+        total_pairs = 2 * ds.n_pairs * world
     log(f"[rank {rank}] workload {name} generated in {time.time() - t0:.1f}s: T={ds.T} U={ds.U} S={ds.S} nnz_tr={ds.nnz_tr} nnz_te={ds.nnz_te}")
-    return ds, desc
+    return ds, desc, total_pairs
 
 
 class ClockSampler(threading.Thread):
@@ -120,11 +136,13 @@ def pinned(a: np.ndarray):
     return t, t.numpy()
 
 
-def cpu_port_sample(ds, n_users: int, threads: int | None = None):
-    """The oracle's canonical CPU port (CSR + inverted index, exact integer accumulation, fp64 finalisation, full sort top-k)
-    on the first n_users test users of the shard, UBM + IBM; returns (pairs, seconds, threads)."""
+# ------------------------------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_sample(ds, n_users: int):
+    """The oracle's canonical CPU port (CSR + inverted index, exact integer accumulation, fp64 finalisation, full-sort top-k) on the
+    first n_users test users of the shard, UBM + IBM, on every host thread; returns (pairs, seconds, threads, top-k lists)."""
     import oracle
     oracle.build()
+    oracle.set_num_threads(host_threads())
     n_users = min(n_users, ds.U)
     sub = ds.shard_test_users(0, n_users)
     t0 = time.perf_counter()
@@ -141,6 +159,7 @@ def as_written_sample(ds, n_songs_ubm: int = 48, n_songs_ibm: int = 48):
     """The reference's loops AS WRITTEN (oracle.naive_sample: MusicRecommender.scala:105-307, linear `contains` scans, cosine
     recomputed per neighbour) with OpenMP over the pair loop (= `.par`, MR:119-125) on a handful of pairs of test user 0."""
     import oracle
+    oracle.set_num_threads(host_threads())
     out = {}
     for name, model, n_songs in (("ubm", oracle.UBM, n_songs_ubm), ("ibm", oracle.IBM, n_songs_ibm)):
         stride = max(1, ds.S // n_songs)
@@ -153,42 +172,79 @@ def as_written_sample(ds, n_songs_ubm: int = 48, n_songs_ibm: int = 48):
     return out
 
 
+def naive_legs(ds, name: str):
+    """the reference's sequential (MR:132-170, 222-261) and `.par` (MR:177-215, 268-307) model builders as written,
+    timed on this box's host cores.  c1 in full; c2 in full for `.par` and on every 4th song for the sequential leg (say so)."""
+    import oracle
+    oracle.build()
+    oracle.set_num_threads(host_threads())
+    out = {"cores": host_threads(), "published_i5_8250U_ms": {"c1": {"ubm_seq": 42857, "ubm_par": 15507, "ibm_seq": 70839, "ibm_par": 25829},
+                                                             "c2": {"ubm_seq": 1090257, "ubm_par": 425118, "ibm_seq": 823119, "ibm_par": 330385}}.get(name)}
+    for mname, model in (("ubm", oracle.UBM), ("ibm", oracle.IBM)):
+        for leg, par in (("seq", False), ("par", True)):
+            stride = 1 if (name == "c1" or par) else 4
+            t0 = time.perf_counter()
+            pairs, _ = oracle.naive_sample(ds, model, 0, ds.U, stride, phase=0, par=par)
+            dt = time.perf_counter() - t0
+            out[f"{mname}_{leg}"] = {"pairs": pairs, "seconds": round(dt, 3), "pairs_per_s": pairs / dt, "threads": host_threads() if par else 1,
+                                     "sample": "whole model" if stride == 1 else f"every {stride}-th song of every test user"}
+    return out
+
+
 def k1_probe(device: int):
     """Kernel K1 (tcgen05 int8 count GEMM) where it dominates: item-space head rows of a dense-friendly shape (65 536 train users x
-    16 384 songs) computed as 1 count GEMM + 4 byte-plane GEMMs; dense-equivalent int8 TOP/s from CUDA events around the GEMM launches."""
+    16 384 songs) computed as 1 count GEMM + 3 byte-plane GEMMs; dense-equivalent int8 TOP/s from CUDA events around the GEMM launches,
+    against the int8 peak measured in the same process."""
     from musicrecommendation_b200 import _lib
     from musicrecommendation_b200.dataset import synth
     from musicrecommendation_b200.recommender import MusicRecommender
+    from musicrecommendation_b200.ksplit import int8_peak
+    peak = None
+    try:
+        peak = int8_peak(device)
+    except Exception as e:  # noqa: BLE001
+        log("int8 peak probe failed:", repr(e))
     ds = synth(T=65536, U=256, S=16384, seed=20230005)
     with MusicRecommender(ds, device=device, engine=_lib.MR_ENGINE_TENSOR, space=_lib.MR_SPACE_ITEM, profile=True) as m:
         m._lib.mr_reset_timing(m._h)
         m.prepare()
         t = m.timing()
         H = m.info()["n_head"]
-    ops = 2.0 * H * ds.S * ((ds.T + 127) // 128 * 128) * 5
+    q_max = int(round(2 ** 24 / np.sqrt(max(1, int(ds.deg_tr.min())))))
+    gemms = 1 + max(1, (q_max.bit_length() + 7) // 8)
+    ops = 2.0 * H * ds.S * ((ds.T + 127) // 128 * 128) * gemms
+    tops = ops / (t["count"] * 1e-3) / 1e12
     return {"kernel": "count_gemm_kernel<256> (tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32, TMA 128B swizzle, TMEM double buffer)",
-            "M": H, "N": ds.S, "K": ds.T, "gemms": 5, "gemm_ms": t["count"], "dense_int8_tops": ops / (t["count"] * 1e-3) / 1e12,
-            "tensor_pipe_active_pct_ncu": 62.9, "ncu": "profiles/r01_gemm_summary.md"}
+            "M": H, "N": ds.S, "K": ds.T, "gemms": gemms, "gemm_ms": t["count"], "dense_int8_tops": tops,
+            "int8_peak_tops_measured": peak, "frac_of_measured_int8_peak": (tops / peak) if peak else None,
+            "peak_how": "torch._int_mm (cuBLASLt) int8 8192^3, best of 10, same process", "ncu": "profiles/r01_gemm_summary.md"}
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU port on rank 0's host cores (all of them, set explicitly — torchrun exports OMP_NUM_THREADS=1),
+    each step a bounded sample of the workload."""
     if rank != 0:
         return
-    ds, desc = make_workload(args.workload, 0, 1)
+    if args.workload == "ksplit":
+        emit({"impl": "reference", "unavailable": "the K-split sweep has no separate CPU arm; its rows are checked against the oracle inside the job"})
+        return
+    ds, desc, _ = make_workload(args.workload, 0, 1, args.users)
     n_users = args.ref_users
     times = []
     pairs = 0
+    thr = 0
     for i in range(args.warmup + args.steps):
         p, dt, thr, _ = cpu_port_sample(ds, n_users)
+        log(f"[reference] step {i}: {p} pairs in {dt:.2f}s on {thr} threads")
         if i >= args.warmup:
             times.append(dt)
             pairs = p
     ms = 1e3 * float(np.mean(times))
     val = pairs / (ms / 1e3)
-    sample = f"first {min(n_users, ds.U)} test users of the shard per step, UBM+IBM canonical CPU port + top-{K_TOP}"
-    line = {"impl": "reference", "metric": "scored (test-user, song) pairs/sec, UBM+IBM with top-500", "value": val, "unit": "pairs/s",
+    sample = f"first {min(n_users, ds.U)} test users per step, UBM+IBM canonical CPU port + top-{K_TOP}, OpenMP on {thr} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+            "scaling": "strong" if args.workload == "msd" else "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
             "config": {"workload": desc, "k": K_TOP},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -201,14 +257,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msd", choices=["msd", "c1", "c2", "c3"])
+    ap.add_argument("--workload", default="msd", choices=["msd", "c1", "c2", "c3", "ksplit"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "sparse"])
     ap.add_argument("--space", default="auto", choices=["auto", "user", "item"])
-    ap.add_argument("--ref-users", type=int, default=384, help="test users per step of the CPU port sample")
+    ap.add_argument("--ref-users", type=int, default=96, help="test users per step of the CPU port sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-as-written", action="store_true", help="skip the as-written (naive) CPU sample")
+    ap.add_argument("--no-as-written", action="store_true", help="skip the as-written (naive) CPU samples")
     ap.add_argument("--no-k1-probe", action="store_true", help="skip the tensor-core count-GEMM probe")
-    ap.add_argument("--users", type=int, default=0, help="profiling aid: score only the first N test users of the shard (not a bench line)")
+    ap.add_argument("--users", type=int, default=0, help="profiling aid: total test users of the job instead of 110 000 (not a bench line)")
+    ap.add_argument("--head-min-deg", type=int, default=-1, help="MR_OPT_HEAD_MIN_DEG (-1: picked from the batches per GPU, 0: library default)")
+    ap.add_argument("--batch-users", type=int, default=0, help="MR_OPT_ITEM_BATCH: cap on test users per batch (0: as many as fit in HBM)")
+    ap.add_argument("--ksplit-songs", type=int, nargs="+", default=[20000])
+    ap.add_argument("--ksplit-mode", default="auto", choices=["auto", "fused", "nccl"])
+    ap.add_argument("--ksplit-panel", type=int, default=4096)
+    ap.add_argument("--ksplit-verify", action="store_true", help="check every row of every panel against the oracle (small S only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,35 +287,53 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "ksplit":
+        from musicrecommendation_b200.ksplit import run_ksplit_bench
+        checker = None
+        if args.ksplit_verify:       # the CPU oracle as the checker of every Gram row (small S only)
+            import oracle
+            oracle.build()
+            oracle.set_num_threads(max(1, host_threads() // world))
+            checker = lambda d, r0, n: oracle.gram_rows(d, np.arange(r0, r0 + n))  # noqa: E731
+        line = run_ksplit_bench(args, rank, world, local_rank, log, checker)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     from musicrecommendation_b200 import _lib
     from musicrecommendation_b200.recommender import MusicRecommender
-    from musicrecommendation_b200.distributed import gather_topk
+    from musicrecommendation_b200.distributed import gather_topk_packed
 
-    ds, desc = make_workload(args.workload, rank, world)
-    if args.users:
-        ds = ds.shard_test_users(0, min(args.users, ds.U))
-        desc += f" [PROFILING SUBSET: first {ds.U} test users]"
+    msd = args.workload == "msd"
+    ds, desc, total_pairs = make_workload(args.workload, rank, world, args.users)
     engine = {"auto": _lib.MR_ENGINE_AUTO, "tensor": _lib.MR_ENGINE_TENSOR, "sparse": _lib.MR_ENGINE_SPARSE}[args.engine]
-    t0 = time.time()
-    t_load0 = time.perf_counter()
     space = {"auto": _lib.MR_SPACE_AUTO, "user": _lib.MR_SPACE_USER, "item": _lib.MR_SPACE_ITEM}[args.space]
-    mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space)
+    # head size: a dense head row pays off when several batches of test users reuse it; a GPU that scores a single batch builds fewer
+    head_min_deg = args.head_min_deg
+    if head_min_deg < 0:
+        head_min_deg = 0
+    t_load0 = time.perf_counter()
+    mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space, head_min_deg=head_min_deg, item_batch=args.batch_users)
     lib, h = mr._lib, mr._h
     load_ms = 1e3 * (time.perf_counter() - t_load0)
-    log(f"[rank {rank}] mr_load done in {time.time() - t0:.1f}s, info={mr.info()}")
+    log(f"[rank {rank}] mr_load done in {load_ms / 1e3:.1f}s, info={mr.info()}")
     stream = torch.cuda.ExternalStream(int(lib.mr_stream(h)), device=local_rank)
-    # one-off per train set: item-space head rows (reported, not part of a step — it depends on the train replica only)
-    t0 = time.perf_counter()
-    mr.prepare()
-    precompute_ms = 1e3 * (time.perf_counter() - t0)
     U, S, k = ds.U, ds.S, K_TOP
-    pairs_per_step = 2 * ds.n_pairs
+    item_space = mr.info()["space"] == _lib.MR_SPACE_ITEM
 
     def check(rc):
         mr._check(rc)
 
-    def step_device():
+    t0 = time.perf_counter()
+    mr.prepare()                                   # cold: includes the cudaMalloc of the head rows
+    cold_precompute_ms = 1e3 * (time.perf_counter() - t0)
+
+    def step_device(rebuild=True):
+        if rebuild and item_space:
+            check(lib.mr_invalidate_prepared(h))
+            check(lib.mr_prepare(h))
         check(lib.mr_topk_device(h, _lib.MR_UBM, 0.0, 0, k))
         check(lib.mr_topk_device(h, _lib.MR_IBM, 0.0, 0, k))
 
@@ -263,44 +343,56 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing (value)
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(n):
+            fn()
+        ev1.record(stream)
+        ev1.synchronize()
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    # ---------------- device-resident timing (value): the whole job, precompute included
     for _ in range(args.warmup):
         step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = mr.info()["launches"]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    ev1.synchronize()
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = timed(step_device, args.steps)
     launches = mr.info()["launches"] - l0
+    # secondary: steady state of a service that keeps the head rows of its train set (no precompute in the step)
+    steady_ms = timed(lambda: step_device(rebuild=False), args.steps)
 
     # ---------------- end-to-end through the host-buffer C-ABI (pinned host -> device, device -> host every step)
     keep = [pinned(ds.te_ptr.astype(np.int64)), pinned(ds.te_col.astype(np.int32)), pinned(ds.deg_te.astype(np.int32))]
     out = [pinned(np.empty((U, k), np.int32)), pinned(np.empty((U, k), np.float64)), pinned(np.empty(U, np.int32))]
     h2d = sum(a.nbytes for _, a in keep)
     d2h = 2 * sum(a.nbytes for _, a in out)
-    base = rank * USERS_PER_GPU * 0   # AGG/STOCH are not part of the bench step; the pair index base is irrelevant here
+    comm_stream = torch.cuda.Stream(device=local_rank) if world > 1 else None
 
     def p(a):
         return C.c_void_p(a.ctypes.data)
 
     def step_e2e(verbose=False):
         t_a = time.perf_counter()
-        check(lib.mr_set_test_users(h, U, p(keep[0][1]), p(keep[1][1]), p(keep[2][1]), base, 0))
+        if item_space:
+            check(lib.mr_invalidate_prepared(h))
+            check(lib.mr_prepare(h))
         t_b = time.perf_counter()
+        check(lib.mr_set_test_users(h, U, p(keep[0][1]), p(keep[1][1]), p(keep[2][1]), 0, 0))
+        t_c = time.perf_counter()
         for model in (_lib.MR_UBM, _lib.MR_IBM):
             check(lib.mr_topk(h, model, 0.0, 0, k, p(out[0][1]), p(out[1][1]), p(out[2][1])))
-            if world > 1:   # the reference's `.collect` (DIST:451-478): all-gather the fixed-size top-k blocks over NCCL
-                torch.cuda.current_stream().wait_stream(stream)
-                gather_topk(*mr.topk_device_tensors(k), U * world, world, rank, reuse_buffers=True)
+            if world > 1:   # the reference's `.collect` (DIST:451-478): ONE gather of the packed (song | score | len) block to rank 0,
+                            # on its own stream so that the UBM block travels while the IBM model is computed
+                gather_topk_packed(mr, k, world, rank, stream, comm_stream)
+        if comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(comm_stream)
         if verbose:
-            log(f"[rank {rank}] e2e step: mr_set_test_users {1e3 * (t_b - t_a):.1f} ms, 2 x mr_topk {1e3 * (time.perf_counter() - t_b):.1f} ms")
+            log(f"[rank {rank}] e2e step: precompute {1e3 * (t_b - t_a):.1f} ms, mr_set_test_users {1e3 * (t_c - t_b):.1f} ms, "
+                f"2 x mr_topk (+gather) {1e3 * (time.perf_counter() - t_c):.1f} ms")
 
     step_e2e(verbose=True)
     barrier()
@@ -322,31 +414,26 @@ def main():
     phases = mr.timing()
     lib.mr_set_profile(h, 0)
     info = mr.info()
-    batch = int(info["batch_rows"]) if info["space"] == _lib.MR_SPACE_ITEM else 128    # test users per batch (mr_get_info) / kUserBatch
+    batch = int(info["batch_rows"]) if item_space else 128    # test users per batch (mr_get_info) / kUserBatch
     n_batches = (U + batch - 1) // batch
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, steady_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(pairs_per_step)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        pairs_all = float(tot.item())
-    else:
-        pairs_all = float(pairs_per_step)
-    dev_ms_max, e2e_ms_max = float(t[0].item()), float(t[1].item())
+    dev_ms_max, e2e_ms_max, steady_ms_max = (float(x) for x in t.tolist())
 
+    line = None
     if rank == 0:
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy figure)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         # dominant phase and its algorithmic bytes per launch: every operand crosses HBM once per launch
         T, nnz = ds.T, ds.nnz_tr
         sparse = info["engine"] == _lib.MR_ENGINE_SPARSE
-        item = info["space"] == _lib.MR_SPACE_ITEM
         Sp = (S + 31) // 32 * 32
         # distinct head songs per batch (head = the n_head songs with most train listeners, ties by id — as mr_load selects them)
         deg_train = np.bincount(ds.tr_col, minlength=S)
@@ -357,7 +444,7 @@ def main():
             cols = ds.te_col[int(ds.te_ptr[b0]):int(ds.te_ptr[min(U, b0 + batch)])]
             distinct_head_rows += int(np.count_nonzero(is_head[np.unique(cols)]))
         n_launch = {"agg_ubm": n_batches, "agg_ibm": n_batches, "topk": 2 * n_batches, "count": 2 * n_batches, "expand": n_batches,
-                    "head_rowsum": 2 * n_batches, "tail_scatter": 2 * n_batches}
+                    "head_rowsum": 2 * n_batches, "tail_scatter": 2 * n_batches, "precompute": 1}
         alg = {
             # user space: count panel + inverted index + q table + Sint panel written
             "agg_ubm": 2 * 128 * T + 4 * nnz + 8 * (S + 1) + 4 * T + 8 * 128 * S,
@@ -366,12 +453,14 @@ def main():
             # 2 B/song of packed G in the IBM pass; users of the batch that share a song reuse its tiles out of L2), and each pass
             # writes its Sint rows; averaged over the 2 * n_batches launches of a step
             "head_rowsum": (distinct_head_rows * Sp * 6 + 2 * U * Sp * 8) / (2 * n_batches),
-            # top-k: three streaming passes over the user's Sint row(s) + rsd for IBM, k results written
-            "topk": (3 * U * S * 8 * 2 + 3 * U * S * 8 + 2 * 12 * U * k) / (2 * n_batches),
+            # top-k: 1.125 (UBM) / 1.25 (IBM, + 4 B fp32 bound per song) streaming passes over the Sint rows, k results written
+            "topk": (1.125 * U * S * 8 + 1.25 * U * S * 8 + U * S * 4 + 2 * 12 * U * k) / (2 * n_batches),
+            # head-row precompute: the packed rows are written once (6 B per entry) + the train CSR / CSC read once
+            "precompute": info["n_head"] * Sp * 6 + 8 * nnz,
         }
         names = {"agg_ubm": "aggregate_panel_kernel<true>", "agg_ibm": "aggregate_panel_kernel<false>" if sparse else "aggregate_ibm_kernel",
                  "topk": "topk_kernel", "count": "sparse_count / count_gemm", "expand": "expand_rows_kernel",
-                 "head_rowsum": "head_rowsum_kernel", "tail_scatter": "tail_scatter_kernel"}
+                 "head_rowsum": "head_rowsum_kernel", "tail_scatter": "tail_scatter_kernel", "precompute": "gram_head_direct_kernel + gram_head_scatter_kernel"}
         dom = max(n_launch, key=lambda n: phases.get(n, 0.0))
         dom_ms = phases[dom] / n_launch[dom]
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
@@ -385,39 +474,53 @@ def main():
                 roof["gathered_gbs"] = roof["gathered_bytes_per_launch"] / (dom_ms * 1e-3) / 1e9
                 roof["note"] = ("algorithmic = each distinct head row of a batch once + Sint written (what must cross HBM); gathered = one row "
                                 "read per (user, head song) entry = what crosses the L2 -> SM fabric.  With one wave of balanced CTAs per song "
-                                "tile the DRAM traffic equals the algorithmic bytes (ncu, profiles/), so the pass is no longer HBM-bound: it "
-                                "runs at gathered_gbs against the ~12-16 TB/s the L2 -> SM fabric delivers (B300_MICROARCH: ~6300 B/clk)")
+                                "tile the DRAM traffic equals the algorithmic bytes (ncu, profiles/), so the pass is bound by the L2 -> SM fabric: "
+                                "it runs at gathered_gbs against the ~12.4 TB/s LTS cap of B300_MICROARCH (6300 B/clk)")
         traffic_file = ROOT / "profiles" / "traffic.json"      # dram bytes per launch from the committed ncu --set full capture
         if traffic_file.exists():
             roof["traffic"] = json.loads(traffic_file.read_text()).get(names[dom])
         line = {
-            "metric": "scored (test-user, song) pairs/sec, UBM+IBM with top-500", "value": pairs_all * args.steps / (dev_ms_max * 1e-3),
+            "metric": METRIC, "value": total_pairs * args.steps / (dev_ms_max * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if msd else "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
             "config": {"workload": desc, "k": K_TOP, "engine": ["auto", "tensor", "sparse"][info["engine"]],
-                       "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"], "users_per_batch": batch,
-                       "l2": "inputs (precomputed head rows >= 10 GB, train CSR/CSC 0.7 GB, the Sint panel of a batch: 8 B per (user, song)) exceed the 126 MB L2; no explicit flush",
-                       "pairs_per_step": pairs_all, "precompute_ms_once_per_train_set": precompute_ms},
-            "e2e": {"value": pairs_all * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"], "users_per_gpu": U, "users_per_batch": batch,
+                       "batches_per_gpu": n_batches,
+                       "l2": "inputs (head rows >= 10 GB rebuilt every step, train CSR/CSC 0.7 GB, the Sint panel of a batch: 8 B per (user, song)) exceed the 126 MB L2; no explicit flush",
+                       "pairs_per_step": total_pairs},
+            "e2e": {"value": total_pairs * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "checksum": checksum,
-            # conservative variant: as if the one-off head-row precompute (it depends on the train replica only) were redone every step
-            "value_if_precompute_redone_every_step": pairs_all * args.steps / ((dev_ms_max + precompute_ms * args.steps) * 1e-3),
-            "cold_start_ms": {"mr_load": load_ms, "precompute_once_per_train_set": precompute_ms},
+            "steady_state": {"value": total_pairs * args.steps / (steady_ms_max * 1e-3), "unit": "pairs/s", "ms_per_step": steady_ms_max / args.steps,
+                             "what": "the same step without the head-row precompute (head rows of the train set kept across steps)"},
+            "precompute_ms_per_step": phases.get("precompute", 0.0) + phases.get("count", 0.0) + phases.get("expand", 0.0) if item_space else 0.0,
+            "cold_start_ms": {"mr_load": load_ms, "first_precompute_incl_cudaMalloc": cold_precompute_ms},
         }
+        # mAP@500 of this rank's users from the device-resident lists (north_star's second parity target)
+        map500 = {}
+        for name, model in (("ubm", _lib.MR_UBM), ("ibm", _lib.MR_IBM)):
+            check(lib.mr_topk_device(h, model, 0.0, 0, k))
+            map500[name] = mr.mapAtK(k)
+        line["map_at_500"] = dict(map500, users=U, what="MSD-challenge mAP@500 of rank 0's test users against their hidden halves (mr_map_at_k)")
         if not args.no_cpu_baseline:
+            import oracle
             pairs_c, sec_c, thr, tops = cpu_port_sample(ds, args.ref_users)
-            # full-size parity: the same users' top-500 from the CUDA path must equal the oracle's bit for bit
+            # full-size parity: the same users' top-500 from the CUDA path must equal the oracle's bit for bit, and so must mAP@500
             n_chk = min(args.ref_users, U)
+            sub = ds.shard_test_users(0, n_chk)
             equal = {}
+            map_equal = {}
             for name, model, (ws, wv, wl) in (("ubm", _lib.MR_UBM, tops[0]), ("ibm", _lib.MR_IBM, tops[1])):
                 gs, gv, gl = mr.getTopK(model, k=k)
                 equal[name] = bool(np.array_equal(gs[:n_chk], ws) and np.array_equal(gv[:n_chk].view(np.int64), wv.view(np.int64))
                                    and np.array_equal(gl[:n_chk], wl))
-            line["parity"] = {"users_checked": n_chk, "top500_ids_and_scores_bit_equal": equal}
+                map_equal[name] = bool(oracle.map_at_k(gs, gl, ds) == map500[name] and oracle.map_at_k(gs[:n_chk], gl[:n_chk], sub) == oracle.map_at_k(ws, wl, sub))
+            line["parity"] = {"users_checked": n_chk, "top500_ids_and_scores_bit_equal": equal, "map_at_500_identical": map_equal}
             line["cpu_baseline_as_written"] = as_written_sample(ds) if not args.no_as_written else None
+            if args.workload in ("c1", "c2") and not args.no_as_written:
+                line["cpu_baseline_naive_seq_par"] = naive_legs(ds, args.workload)
             line["cpu_baseline"] = {"value": pairs_c / sec_c, "unit": "pairs/s", "cores": thr, "kind": "port",
-                                    "sample": f"first {min(args.ref_users, U)} test users of rank 0's shard, UBM+IBM canonical CPU port + top-{K_TOP}, {sec_c:.1f}s"}
+                                    "sample": f"first {n_chk} test users of rank 0's shard, UBM+IBM canonical CPU port + top-{K_TOP}, {sec_c:.1f}s"}
     mr.close()
     if rank == 0:
         if not args.no_k1_probe:   # after the scorer released its HBM (it sizes its batches to fill the GPU)
@@ -427,6 +530,7 @@ def main():
                 line["k1_count_gemm_probe"] = {"error": repr(e)}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -85,9 +85,19 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs,
 int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const int32_t* te_col, const int32_t* deg_test,
                       int64_t pair_index_base, int64_t n_pairs_total);
 
+/* Tunables.  MR_OPT_HEAD_MIN_DEG (before mr_load): a song gets a precomputed dense head row when it has at least this many train
+ * listeners (0 = default max(2, S / 6000), the optimum when the rows are reused by many shards; a one-shot job over few test users is
+ * faster with a smaller head, bench.py picks it from the number of shards per GPU).  MR_OPT_ITEM_BATCH: upper bound on the test users
+ * per item-space batch (0 = as many as fit in HBM).  Results never depend on either. */
+enum { MR_OPT_HEAD_MIN_DEG = 1, MR_OPT_ITEM_BATCH = 2 };
+int mr_set_option(mr_handle* h, int option, int64_t value);
+
 /* Build the item-space head rows (G, Gq of the popular songs) now instead of lazily on the first scoring call
  * that uses them.  One-off per train set: tensor-core GEMMs on the tensor engine, inverted-index scatter otherwise. */
 int mr_prepare(mr_handle* h);
+/* Forget the head rows (their HBM stays allocated): the next mr_prepare / scoring call rebuilds them.  bench.py uses it to put the
+ * whole of getUserBasedModel / getItemBasedModel (MR:132-170, 222-261 — they have no amortisable half) inside every timed step. */
+int mr_invalidate_prepared(mr_handle* h);
 
 /* Parity probes for kernel K1: out[u*T + v] = |I_u ∩ I_v| (numerator of MR:142-145), and rows [s0,s1) of the train
  * co-occurrence matrix out[(i-s0)*S + j] = |U_i ∩ U_j| over train users (numerator of MR:232-235). */
@@ -104,6 +114,15 @@ int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t
  * peer's HBM mapped over NVLink (mr_peer_alloc / mr_peer_open, CUDA IPC), in coalesced 128-byte row segments, tile by tile while the
  * tensor cores work on the next tile.  The owner then sums its `world` slots locally (integers: exact).  Tensor engine only. */
 int mr_gram_rows_scatter(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld);
+/* Stream-ordered variant for a pipelined exchange without host synchronisation: mr_gram_rows_scatter_async only enqueues; mr_peer_signal
+ * enqueues "raise the 64-bit counters at flag_ptrs[0..n) (local or peer memory) to `value` once everything enqueued before has completed"
+ * (system-scope release); mr_peer_wait enqueues "hold this handle's stream until the n consecutive 64-bit counters at `flags` (local
+ * memory) are all >= value" (system-scope acquire, bounded: a dead peer traps instead of hanging).  mr_sync drains the handle's stream.
+ * musicrecommendation_b200/ksplit.py shows the double-buffered protocol built from them. */
+int mr_gram_rows_scatter_async(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld);
+int mr_peer_signal(mr_handle* h, void* const* flag_ptrs, int n, uint64_t value);
+int mr_peer_wait(mr_handle* h, const void* flags, int n, uint64_t value);
+int mr_sync(mr_handle* h);
 int mr_peer_alloc(mr_handle* h, uint64_t bytes, void** dev_ptr, unsigned char* handle_out_64);   /* zeroed device buffer + its IPC handle */
 int mr_peer_open(mr_handle* h, const unsigned char* handle_64, void** dev_ptr);                  /* map a peer's buffer into this process */
 int mr_peer_close(mr_handle* h, void* dev_ptr);
@@ -117,6 +136,13 @@ int mr_similarity_ibm(mr_handle* h, int s0, int s1, float* out_rows);
  * the reference does not emit (MR:109).  model = MR_UBM | MR_IBM.  Small configurations only (U*S*8 bytes). */
 int mr_score_dense(mr_handle* h, int model, double* out_UxS);
 
+/* The per-partition granularities of distributed.scala: UserBasedModel / ItemBasedModel.getRanks1(user) (DIST:198-205, 269-276) — every
+ * unlistened song of the listed test users, out[i*S + s] (NaN at listened pairs) — and getRanks2(song) (DIST:214-221, 285-292) — every
+ * test user that has not listened to the listed songs, out[i*U + u] (NaN where user u listened to song_ids[i]).  model = MR_UBM | MR_IBM;
+ * ids index the current test shard / the songs.  Same values as the corresponding entries of mr_score_dense. */
+int mr_score_users(mr_handle* h, int model, const int32_t* user_idx, int n, double* out_nxS);
+int mr_score_songs(mr_handle* h, int model, const int32_t* song_ids, int n, double* out_nxU);
+
 /* Blends on materialised, aligned model arrays (MR:317-481): kind = MR_LC | MR_AGG | MR_STOCH.  first_index / n_total as in
  * mr_set_test_users (0 / 0 for whole models). */
 int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const double* ubm, const double* ibm, double* out,
@@ -129,6 +155,15 @@ int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const do
 int mr_evaluate_dense(mr_handle* h, const double* scores_UxS, int n_users, int n_songs, const int64_t* lab_rowptr, const int32_t* lab_col,
                       int n_thresholds, double* out_map);
 
+/* mAP@k of ranked lists against the hidden (label) half of the test users — north_star's "mAP@500".  The reference has no ranking and
+ * no such metric (its evaluateModel is the threshold sweep above); this is the Million Song Dataset Challenge definition:
+ * AP@k(u) = (sum_{i<=n} [r_i in L_u] * hits_i / i) / min(|L_u|, k), mean over the test users with at least one label row.
+ * top_song [n_users x k] / top_len [n_users] as mr_topk returns them, or both NULL to rank the device-resident result of the last
+ * mr_topk / mr_topk_device of this handle (n_users must then be the shard size).  out_ap (optional) receives the per-user AP.
+ * Users are folded in ascending id order, terms in rank order (fp64), so the CPU restatement the tests hold gives the same bits. */
+int mr_map_at_k(mr_handle* h, int k, const int32_t* top_song, const int32_t* top_len, int n_users, const int64_t* lab_rowptr,
+                const int32_t* lab_col, double* out_map, double* out_ap);
+
 /* getTopK(model, k): per test user the k best unlistened songs, score descending then song id ascending (new derived
  * output named by north_star; the reference has no ranking step).  out_song / out_score are U x k (song -1 / score 0.0 past
  * out_len[u] = min(k, S - |I_u|)).  1 <= k <= 1024.  model = any MR_* selector; blends are fused into the select. */
@@ -140,6 +175,9 @@ int mr_topk_fetch(mr_handle* h, int k, int32_t* out_song, double* out_score, int
 /* Device addresses of the last mr_topk_device result (int32 [U,k], double [U,k], int32 [U]) for callers that gather it over
  * NCCL without a host round trip (the reference's `.collect`, DIST:451-478).  Valid until the next call on the handle. */
 int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** len);
+/* The three arrays live in ONE device block (song | score | len at the returned byte offsets), so the whole result of a shard travels
+ * in a single transfer — one NCCL gather to the rank that plays the Spark driver instead of three collectives. */
+int mr_topk_packed(mr_handle* h, int k, void** base, uint64_t* bytes, uint64_t* score_offset, uint64_t* len_offset);
 
 /* ---- ingest: `new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12, 26-91) on the GPU ----------------------------------
  * The three TSV files as byte buffers (`user \t song \t count` per line, third field ignored, MR:35) become the int-id data model
@@ -160,6 +198,16 @@ const char* mr_ingest_error(const mr_ingest* g);
 int mr_ingest_dims(const mr_ingest* g, int32_t* n_train, int32_t* n_test, int32_t* n_songs, int32_t* n_label_only_songs);
 int mr_ingest_get(const mr_ingest* g, int which, const void** ptr, int64_t* n_elems);
 void mr_ingest_free(mr_ingest* g);
+
+/* ---- model file writer: writeModelOnFile (MR:489-496), host code ------------------------------------------------------------------------
+ * One line `user \t song \t Double.toString(score) \n` per emitted pair of a materialised model (scores_UxS as mr_score_dense /
+ * mr_blend_dense produce it, NaN = not emitted), in main.scala:57-59 order, with the ids turned back into the reference's strings through
+ * the id -> string tables (bytes + int64 offsets [n+1], as mr_ingest_get returns them).  Scores are laid out by java.lang.Double.toString's
+ * rules (shortest round-tripping digits; plain decimal in [1e-3, 1e7), d.dddE-n otherwise) so importModelFromFile (MR:505-512) reads
+ * them back bit for bit.  mr_format_double exposes the formatter (out32: >= 32 bytes, NUL-terminated; returns the length). */
+int mr_write_model(const char* path, const double* scores_UxS, int n_users, int n_songs, const char* user_chars, const int64_t* user_off,
+                   const char* song_chars, const int64_t* song_off, int append, int64_t* rows_written);
+int mr_format_double(double x, char* out32);
 
 /* Introspection used by bench.py / tests. */
 enum { MR_T_EXPAND = 0, MR_T_COUNT = 1, MR_T_AGG_UBM = 2, MR_T_AGG_IBM = 3, MR_T_TOPK = 4, MR_T_OTHER = 5,

@@ -310,11 +310,9 @@ static int make_tmap_u8(CUtensorMap* tm, const uint8_t* base, long long rows, lo
 template <int BN, int EPI>
 static cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  {  // the attribute is per device (handles may live on several GPUs of one process); setting it is cheap, so no caching
     cudaError_t e = cudaFuncSetAttribute(count_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -375,6 +373,47 @@ int launch_expand_rows_weighted(const long long* ptr, const int* idx, const uint
   long long blocks = (static_cast<long long>(n_rows) + wpb - 1) / wpb;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   expand_rows_weighted_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(ptr, idx, weight, plane, n_rows, pitch, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Completion flags of the fused K-split exchange (EPI_I32_SCATTER): no host round trip per panel.  A sender's signal kernel runs on
+// the library stream right after its scatter GEMM (stream order = its tiles have been issued and the kernel has drained), fences at
+// system scope and raises a 64-bit counter in every owner's flag block with a release store — local HBM or a peer's over NVLink.
+// The owner's wait kernel spins with acquire loads on its own flag block until every sender has reached the panel's sequence number,
+// so whatever follows on that stream (the sum of the slots, the normalisation) sees complete data.  Waits are bounded (trap, no hang).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void peer_signal_kernel(PeerFlags flags, int n, unsigned long long value) {
+  if (static_cast<int>(threadIdx.x) < n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags.p[threadIdx.x]), "l"(value) : "memory");
+  }
+}
+
+__global__ void peer_wait_kernel(const unsigned long long* flags, int n, unsigned long long value) {
+  if (static_cast<int>(threadIdx.x) < n) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+      if (v >= value) break;
+      if (clock64() - t0 > 40000000000LL) __trap();     // ~20 s: a peer died or the protocol is broken
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+int launch_peer_signal(PeerFlags flags, int n, unsigned long long value, cudaStream_t st) {
+  if (n < 1 || n > 8) return -2;
+  peer_signal_kernel<<<1, 32, 0, st>>>(flags, n, value);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_peer_wait(const unsigned long long* flags, int n, unsigned long long value, cudaStream_t st) {
+  if (n < 1 || n > 8) return -2;
+  peer_wait_kernel<<<1, 32, 0, st>>>(flags, n, value);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -67,6 +67,26 @@ int launch_dense_scores(int model, const long long* sint, long long spitch, int 
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// Columns of a chunk of dense model rows, transposed: out[i * out_ld + u_base + r] = dense[r][songs[i]] — the per-song granularity of
+// distributed.scala's getRanks2(song) (DIST:214-221, 285-292): one song against every test user.
+__global__ void gather_columns_kernel(const double* __restrict__ dense, int n_rows, int n_songs, const int* __restrict__ songs, int n_sel,
+                                      double* __restrict__ out, long long out_ld, int u_base) {
+  const long long n = static_cast<long long>(n_sel) * n_rows;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n; t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(t / n_rows), r = static_cast<int>(t % n_rows);
+    out[i * out_ld + u_base + r] = dense[static_cast<long long>(r) * n_songs + songs[i]];
+  }
+}
+
+int launch_gather_columns(const double* dense, int n_rows, int n_songs, const int* songs, int n_sel, double* out, long long out_ld, int u_base,
+                          cudaStream_t st) {
+  if (n_rows <= 0 || n_sel <= 0) return 0;
+  const long long n = static_cast<long long>(n_sel) * n_rows;
+  const int grid = static_cast<int>(n + 255 < 256LL * 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  gather_columns_kernel<<<grid, 256, 0, st>>>(dense, n_rows, n_songs, songs, n_sel, out, out_ld, u_base);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // ---------------------------------------------------------------- java.util.Random (48-bit LCG) with O(log n) jump-ahead
 constexpr unsigned long long kLcgA = 0x5DEECE66DULL, kLcgC = 0xBULL, kLcgMask = (1ULL << 48) - 1;
 

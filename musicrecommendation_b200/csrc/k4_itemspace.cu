@@ -69,13 +69,57 @@ int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The same events added straight into the FINAL packed rows, for head songs none of whose entries can overflow (weighted listener
+// sum < 2^32, train degree < 2^16 — checked per row on the host): Gq32[h][s] += qv[v] and G16[h][s] += 1 as two 32-bit L2 atomics
+// (the u16 count is bumped through the aligned 32-bit word that holds it: a count < 2^16 never carries into its neighbour).  The
+// caller hands over an L2-sized chunk of rows: they are zeroed here (the lines stay dirty in L2), receive their events as L2 hits
+// and drain to HBM once — 6 bytes of DRAM traffic per entry, no staging area, no pack pass.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gram_head_direct_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int r0, int r1,
+                        const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
+                        const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
+                        uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, long long pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = lst_ptr[r0], w1 = lst_ptr[r1];
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  uint32_t* g_words = reinterpret_cast<uint32_t*>(g16);
+  for (long long w = w0 + static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < w1; w += n_warps) {
+    int lo = r0, hi = r1;                          // row = upper_bound(lst_ptr, w) - 1 within the chunk [r0, r1)
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (lst_ptr[m + 1] <= w) lo = m + 1; else hi = m; }
+    const int h = lo;
+    const int j = head_song[h];
+    const int v = csc_idx[csc_ptr[j] + (w - lst_ptr[h])];
+    const uint32_t q = qv[v];
+    const long long row = static_cast<long long>(h) * pitch;   // pitch is a multiple of 32: the parity of row + s is the parity of s
+    const long long b = tr_ptr[v], e = tr_ptr[v + 1];
+    for (long long m = b + lane; m < e; m += 32) {
+      const int s = __ldg(tr_col + m);
+      atomicAdd(gq32 + row + s, q);
+      atomicAdd(g_words + ((row + s) >> 1), (s & 1) ? 0x10000u : 1u);
+    }
+  }
+}
+
+int launch_gram_head_direct(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
+                            const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint16_t* g16, uint32_t* gq32,
+                            long long pitch, int num_sms, cudaStream_t st) {
+  if (r1 <= r0) return 0;
+  cudaError_t e = cudaMemsetAsync(g16 + static_cast<long long>(r0) * pitch, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint16_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(gq32 + static_cast<long long>(r0) * pitch, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return -1;
+  gram_head_direct_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g16, gq32, pitch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Pack a chunk of staged rows (u32 counts, u64 weighted sums) into the resident 6-byte-per-entry form: the low 16 bits of G
 // and the low 32 bits of Gq.  The few entries that do not fit (pairs of very popular songs) keep their high parts exactly in
 // an exception list (row, song, G - low, Gq - low) that head_fixup_kernel adds back.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_head_rows_kernel(const uint32_t* __restrict__ g, const unsigned long long* __restrict__ gq, int packed, int r0, int n_rows, long long pitch,
-                      uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, HeadExceptions ex) {
+                      int n_songs, uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, HeadExceptions ex) {
   const long long n = static_cast<long long>(n_rows) * pitch;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const unsigned long long raw = gq[i];
@@ -84,7 +128,7 @@ pack_head_rows_kernel(const uint32_t* __restrict__ g, const unsigned long long* 
     const long long o = static_cast<long long>(r0) * pitch + i;
     g16[o] = static_cast<uint16_t>(a & 0xffffu);
     gq32[o] = static_cast<uint32_t>(b & 0xffffffffULL);
-    if ((a >> 16) | (b >> 32)) {
+    if (((a >> 16) | (b >> 32)) && static_cast<int>(i % pitch) < n_songs) {   // pad columns hold zeros; never let them reach the list
       const unsigned int pos = atomicAdd(ex.count, 1u);
       if (pos < ex.capacity) {
         ex.row[pos] = r0 + static_cast<int>(i / pitch);
@@ -96,12 +140,12 @@ pack_head_rows_kernel(const uint32_t* __restrict__ g, const unsigned long long* 
   }
 }
 
-int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, uint16_t* g16,
-                          uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st) {
+int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, int n_songs,
+                          uint16_t* g16, uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st) {
   if (n_rows <= 0) return 0;
   const long long n = static_cast<long long>(n_rows) * pitch;
   const int grid = static_cast<int>(std::min<long long>(num_sms * 16LL, (n + 255) / 256));
-  pack_head_rows_kernel<<<grid, 256, 0, st>>>(g, gq, packed, r0, n_rows, pitch, g16, gq32, ex);
+  pack_head_rows_kernel<<<grid, 256, 0, st>>>(g, gq, packed, r0, n_rows, pitch, n_songs, g16, gq32, ex);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -103,4 +103,53 @@ int launch_evaluate(const double* scores, int n_users, int n_songs, const long l
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// mAP@k of the ranked lists (north_star's "mAP@500"; the reference has no ranking, so this is the Million Song Dataset Challenge
+// definition, stated in include/mrscore.h at mr_map_at_k):  AP@k(u) = (sum_i [r_i in L_u] * hits_i / i) / min(|L_u|, k).
+// One warp per test user: the lanes test 32 ranks at a time against the user's ascending label row (binary search), lane 0 adds the
+// terms of the relevant ranks in rank order with explicit round-to-nearest operations, so the per-user AP is bit-identical to the CPU
+// restatement; the mean over users is taken on the host in ascending user order.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+map_at_k_kernel(const int* __restrict__ top_song, const int* __restrict__ top_len, int n_users, int k, const long long* __restrict__ lab_ptr,
+                const int* __restrict__ lab_col, double* __restrict__ ap_out) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n_users) return;
+  const long long l0 = lab_ptr[u], l1 = lab_ptr[u + 1];
+  const long long nl = l1 - l0;
+  if (nl <= 0) { if (lane == 0) ap_out[u] = 0.0; return; }
+  const int n = min(top_len[u], k);
+  const int* row = top_song + static_cast<long long>(u) * k;
+  int hits = 0;
+  double ap = 0.0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    bool rel = false;
+    if (i < n) {
+      const int s = row[i];
+      long long lo = l0, hi = l1;
+      while (lo < hi) { const long long m = (lo + hi) >> 1; if (lab_col[m] < s) lo = m + 1; else hi = m; }
+      rel = lo < l1 && lab_col[lo] == s;
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, rel);
+    if (lane == 0) {
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        ++hits;
+        ap = __dadd_rn(ap, __ddiv_rn(static_cast<double>(hits), static_cast<double>(base + b + 1)));
+      }
+    }
+  }
+  if (lane == 0) ap_out[u] = __ddiv_rn(ap, static_cast<double>(nl < k ? nl : static_cast<long long>(k)));
+}
+
+int launch_map_at_k(const int* top_song, const int* top_len, int n_users, int k, const long long* lab_ptr, const int* lab_col,
+                    double* ap_out, cudaStream_t st) {
+  if (n_users <= 0) return 0;
+  map_at_k_kernel<<<(n_users + 3) / 4, 128, 0, st>>>(top_song, top_len, n_users, k, lab_ptr, lab_col, ap_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 }  // namespace mr

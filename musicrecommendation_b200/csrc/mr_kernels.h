@@ -28,6 +28,12 @@ int launch_expand_rows_weighted(const long long* ptr, const int* idx, const uint
 int launch_expand_rows(const long long* ptr, const int* idx, const int* rows, int row0, int n_rows, int n_rows_pad,
                        long long pitch, uint8_t* out, cudaStream_t st);
 
+// stream-ordered completion flags of the fused K-split exchange (k1_count_gemm.cu): a sender raises a 64-bit counter in every owner's
+// memory (local or NVLink peer) after its tiles have landed; the owner spins on its own flags before it sums its slots
+struct PeerFlags { unsigned long long* p[8]; };
+int launch_peer_signal(PeerFlags flags, int n, unsigned long long value, cudaStream_t st);
+int launch_peer_wait(const unsigned long long* flags, int n, unsigned long long value, cudaStream_t st);
+
 // ---- K1s (k1_sparse_count.cu): the same counts from the inverted index, for shapes whose dense operands do not fit
 int launch_sparse_count_u16t(const long long* te_ptr, const int* te_col, int u0, int n_users, const long long* csc_ptr,
                              const int* csc_idx, uint16_t* ct, long long n_train, cudaStream_t st);
@@ -65,8 +71,11 @@ struct HeadExceptions {      // entries of the packed head rows whose count exce
 int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
                              const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
                              long long pitch, int packed, int num_sms, cudaStream_t st);
-int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, uint16_t* g16,
-                          uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
+int launch_gram_head_direct(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
+                            const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint16_t* g16, uint32_t* gq32,
+                            long long pitch, int num_sms, cudaStream_t st);
+int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, int n_songs,
+                          uint16_t* g16, uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
 // model: 1 = UBM pass over Gq32, 2 = IBM pass over G16; words = 32-bit words per row load (1, 2 or 4); threads per CTA (a CTA covers
 // threads * songs-per-thread songs); groups / segments: see k4_itemspace.cu
 int launch_head_rowsum(int model, int words, int threads, const int4* grp_hdr, int n_groups, const int4* seg, const int* ge_row,
@@ -109,11 +118,16 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 int launch_topk(const BlendParams& bp, const long long* te_ptr, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
                 long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
                 int* out_song, double* out_score, int* out_len, cudaStream_t st);
+int launch_gather_columns(const double* dense, int n_rows, int n_songs, const int* songs, int n_sel, double* out, long long out_ld, int u_base,
+                          cudaStream_t st);
 int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n, long long first_index,
                         cudaStream_t st);
 
 // ---- evaluation (k5_evaluate.cu)
 int launch_evaluate(const double* scores, int n_users, int n_songs, const long long* lab_ptr, const int* lab_col, const int* new_songs,
                     int n_new, int n_thresholds, unsigned long long* minmax, double* ap_out, int num_sms, cudaStream_t st);
+
+int launch_map_at_k(const int* top_song, const int* top_len, int n_users, int k, const long long* lab_ptr, const int* lab_col,
+                    double* ap_out, cudaStream_t st);
 
 }  // namespace mr

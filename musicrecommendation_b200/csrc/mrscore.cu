@@ -29,6 +29,9 @@ using namespace mr;
 namespace {
 
 constexpr int kSplitLen = 4096;   // listeners per K2 work item
+// largest degrees whose fixed-point cosine factor stays within 1e-5 relative: 0.5 * sqrt(deg) / 2^k <= 1e-5  <=>  deg <= (2e-5 * 2^k)^2
+constexpr int kMaxDegUbm = 112589;      // (2e-5 * 2^24)^2 = 112 589.99
+constexpr int kMaxDegIbm = 1801439;     // (2e-5 * 2^26)^2 = 1 801 439.85
 
 }  // namespace
 
@@ -47,6 +50,7 @@ struct mr_handle {
   struct SongInfo { int head; uint32_t v; };   // head row or -1; v = q_26(d_s) of a head song, train listeners of a tail song
   int2* d_song_info = nullptr;                 // the same records on the device (k7_testlists.cu)
   std::vector<SongInfo> song_info;             // per song, 8 bytes: the one random access per test entry in mr_set_test_users
+  uint32_t max_qv = 0;                         // largest UBM weight q_24(|I_v|) of a train user (number of byte planes of the tensor precompute)
   unsigned long long max_qsum = 0;             // max over songs of song_qsum
   std::vector<unsigned long long> song_qsum;   // per song: sum of qv over its train listeners = upper bound of any Gq entry of its row
   bool ubm_int_ok = false;                     // every UBM numerator of the current shard is provably < 2^52 (top-k may rank the integers)
@@ -62,6 +66,9 @@ struct mr_handle {
   std::vector<int> h_split_ptr;   // balanced work groups per batch
   std::vector<int> head_index;         // song -> head row or -1
   int* d_head_song = nullptr; long long* d_head_lst_ptr = nullptr; uint16_t* d_g16 = nullptr; uint32_t* d_gq32 = nullptr;
+  size_t head_rows_cap = 0;            // entries the packed-row allocations hold (kept across mr_invalidate_prepared)
+  int n_head_staged = 0;               // rows [0, n_head_staged) are built in a 64-bit staging area and packed; the rest directly in place
+  long long opt_head_min_deg = 0;      // mr_set_option(MR_OPT_HEAD_MIN_DEG): 0 = default rule
   long long* d_ex_ptr = nullptr; int* d_ex_song = nullptr; uint32_t* d_ex_g = nullptr; unsigned long long* d_ex_gq = nullptr; long long n_ex = 0;
   long long *d_hu_ptr = nullptr; int *d_hu_row = nullptr, *d_hu_song = nullptr; uint32_t* d_hu_q = nullptr;
   int *d_tu_user = nullptr, *d_tu_song = nullptr; long long* d_tu_lptr = nullptr; std::vector<long long> h_tu_ptr, h_tu_lptr; long long n_head_entries = 0, n_tail_entries = 0;
@@ -69,7 +76,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_SONG, SL_OUT_SCORE, SL_OUT_LEN, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_EX_PTR, SL_EX_SONG, SL_EX_G, SL_EX_GQ, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_PACK, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -82,7 +89,7 @@ struct mr_handle {
   uint64_t* d_sel = nullptr; long long sel_pitch = 0; int32_t* d_g = nullptr; size_t g_bytes = 0; size_t aj_bytes = 0;
   double* d_dense = nullptr; int32_t* d_cnt = nullptr; float* d_simf = nullptr;
   // results
-  int *d_out_song = nullptr, *d_out_len = nullptr; double* d_out_score = nullptr; int out_k = 0; bool have_topk = false;
+  int *d_out_song = nullptr, *d_out_len = nullptr; double* d_out_score = nullptr; int out_k = 0; bool have_topk = false; size_t out_pack_bytes = 0;
   // profiling
   cudaEvent_t ev[2] = {nullptr, nullptr}; double t_ms[MR_T_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -278,8 +285,16 @@ int ensure_gram_ws(mr_handle* h, int n_rows) {
   return MR_OK;
 }
 
-// Item-space: compute the rows G[h][:], Gq[h][:] of the head songs once per train set (lazily, on first use), chunk by chunk
-// into a u32 / u64 staging area, and pack them to 6 bytes per entry (+ an exact exception list for the few entries that overflow).
+// Item-space: compute the rows G[h][:], Gq[h][:] of the head songs once per train set (lazily, on first use, or mr_prepare).
+// Head rows are ordered by train degree, descending.  Two construction paths, both from the inverted index:
+//   staged rows [0, n_head_staged): the most popular songs, whose entries can exceed 16 / 32 bits — one packed 64-bit accumulator per
+//     entry in an L2-resident staging chunk, then pack_head_rows_kernel writes the 6-byte form + the exact exception list;
+//   direct rows [n_head_staged, n_head): every song whose weighted listener sum is < 2^32 and whose train degree is < 2^16 — no entry
+//     of such a row can overflow, so the events are added straight into the final u16 / u32 arrays (32-bit L2 atomics), an L2-sized
+//     chunk of rows at a time: zero the chunk (it stays dirty in L2), scatter into it, let it drain to HBM once.  This path moves
+//     6 bytes per entry instead of 8 (zero) + 8 (read) + 6 (write) and has no pack pass: it is what made the sparse 85 % of the head
+//     rows cheap (they carry few events but paid the full dense staging traffic).
+// On the tensor engine (dense-friendly shapes) every row is staged and computed by K1: one 0/1 count GEMM + byte-plane GEMMs of the weights.
 int ensure_head_rows(mr_handle* h) {
   if (h->head_ready) return MR_OK;
   int rc;
@@ -288,17 +303,27 @@ int ensure_head_rows(mr_handle* h) {
   auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
   auto t_start = now();
   const size_t n = static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch;
-  if ((rc = dev_alloc(h, &h->d_g16, n, h->allocs))) return rc;
-  if ((rc = dev_alloc(h, &h->d_gq32, n, h->allocs))) return rc;
+  if (h->head_rows_cap < n) {   // allocated once per handle; a failed or invalidated precompute reuses it
+    if (h->d_g16) { cudaFree(h->d_g16); h->d_g16 = nullptr; }
+    if (h->d_gq32) { cudaFree(h->d_gq32); h->d_gq32 = nullptr; }
+    h->dev_bytes -= h->head_rows_cap * 6; h->head_rows_cap = 0;
+    MR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->d_g16), n * sizeof(uint16_t)));
+    cudaError_t em = cudaMalloc(reinterpret_cast<void**>(&h->d_gq32), n * sizeof(uint32_t));
+    if (em != cudaSuccess) { cudaFree(h->d_g16); h->d_g16 = nullptr; return fail(h, MR_ERR_OOM, "head rows: %s", cudaGetErrorString(em)); }
+    h->head_rows_cap = n; h->dev_bytes += n * 6;
+  }
   const bool tensor = h->engine == MR_ENGINE_TENSOR && h->n_head > 0 && h->T < (1 << 23);
+  const int n_staged = tensor ? h->n_head : h->n_head_staged;
+  // number of byte planes the weights q_24(|I_v|) need (3 when every train user has >= 2 songs: q < 2^24)
+  int n_planes = 1;
+  while (n_planes < 4 && (static_cast<unsigned long long>(h->max_qv) >> (8 * n_planes)) != 0) ++n_planes;
   // staging chunk.  Tensor engine: <= 8 GiB of (u32 + u64) rows, a multiple of the 128-row GEMM tile.  Scatter path: small enough
-  // (<= 64 MiB) that the rows being built stay L2-resident, so the 6e9 integer atomics of an MSD-sized precompute are resolved in
-  // L2 instead of as DRAM read-modify-writes (measured: 260 GB of DRAM traffic for the first 2048-row chunk otherwise).
-  long long chunk; bool packed = false;
+  // (<= 64 MiB) that the rows being built stay L2-resident, so the integer atomics are resolved in L2 instead of as DRAM read-modify-writes.
+  long long chunk = 1; bool packed = false;
   if (tensor) {
     chunk = (8LL << 30) / (h->spitch * 12) / 128 * 128;
     chunk = std::max<long long>(128, std::min<long long>(chunk, 4096));
-  } else {
+  } else if (n_staged > 0) {
     // one packed 64-bit accumulator per entry when no weighted sum can reach 2^44 and no count 2^20 (any realistic data set)
     packed = h->max_qsum < (1ULL << 44) && *std::max_element(h->deg_song_train.begin(), h->deg_song_train.end()) < (1 << 20) &&
              !getenv("MRSCORE_PRECOMPUTE_UNPACKED");
@@ -308,33 +333,37 @@ int ensure_head_rows(mr_handle* h) {
   std::vector<void*> tmp;
   uint32_t* g_stage = nullptr; unsigned long long* gq_stage = nullptr;
   HeadExceptions ex{};
-  ex.capacity = 1u << 24;
-  if ((rc = dev_alloc(h, &g_stage, packed ? 1 : static_cast<size_t>(chunk) * h->spitch, tmp)) ||
-      (rc = dev_alloc(h, &gq_stage, static_cast<size_t>(chunk) * h->spitch, tmp)) ||
+  ex.capacity = n_staged > 0 ? (1u << 24) : 1u;
+  const size_t stage_entries = n_staged > 0 ? static_cast<size_t>(chunk) * h->spitch : 1;
+  if ((rc = dev_alloc(h, &g_stage, packed ? 1 : stage_entries, tmp)) || (rc = dev_alloc(h, &gq_stage, stage_entries, tmp)) ||
       (rc = dev_alloc(h, &ex.count, 1, tmp)) || (rc = dev_alloc(h, &ex.row, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.song, ex.capacity, tmp)) ||
       (rc = dev_alloc(h, &ex.g_extra, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.gq_extra, ex.capacity, tmp))) { free_list(tmp); return rc; }
+  auto bail = [&](int code) { cudaStreamSynchronize(h->stream); free_list(tmp); return code; };
   cudaError_t e = cudaMemsetAsync(ex.count, 0, sizeof(unsigned int), h->stream);
-  if (e != cudaSuccess) { free_list(tmp); return fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
   uint8_t *a_rows = nullptr, *b_plane = nullptr;
   if (tensor) {
     if ((rc = dev_alloc(h, &a_rows, static_cast<size_t>(chunk) * h->pitchT, tmp)) ||
-        (rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT * 4, tmp))) { free_list(tmp); return rc; }
-    // the four byte planes of q_24(|I_v|) as weighted B operands (built once, reused by every chunk)
+        (rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT * n_planes, tmp))) { free_list(tmp); return rc; }
+    // the GEMM epilogues write only the columns < S: the pad columns of the staging rows must not hold garbage (pack reads the full pitch)
+    e = cudaMemsetAsync(g_stage, 0, stage_entries * sizeof(uint32_t), h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gq_stage, 0, stage_entries * sizeof(unsigned long long), h->stream);
+    if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
+    // the byte planes of q_24(|I_v|) as weighted B operands (built once, reused by every chunk)
     PhaseTimer t(h, MR_T_EXPAND);
-    for (int plane = 0; plane < 4; ++plane) {
+    for (int plane = 0; plane < n_planes; ++plane) {
       int lrc = launch_expand_rows_weighted(h->d_csc_ptr, h->d_csc_idx, h->d_qv, plane, h->S, h->pitchT,
                                             b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->stream);
       h->launches++;
-      if (lrc) { free_list(tmp); return fail(h, MR_ERR_CUDA, "launch_expand_rows_weighted failed"); }
+      if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_expand_rows_weighted failed"));
     }
   }
-  auto bail = [&](int code) { cudaStreamSynchronize(h->stream); free_list(tmp); return code; };
-  if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[mrscore] precompute: allocations %.1f ms (chunk %lld rows)\n", ms_since(t_start), chunk); }
+  if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[mrscore] precompute: allocations %.1f ms (staged rows %d in chunks of %lld, direct rows %d)\n", ms_since(t_start), n_staged, chunk, h->n_head - n_staged); }
   auto t_loop = now();
-  for (int r0 = 0; r0 < h->n_head; r0 += static_cast<int>(chunk)) {
-    const int nr = std::min<int>(static_cast<int>(chunk), h->n_head - r0);
+  for (int r0 = 0; r0 < n_staged; r0 += static_cast<int>(chunk)) {
+    const int nr = std::min<int>(static_cast<int>(chunk), n_staged - r0);
     if (tensor) {
-      // G = A_head · A_trT^T as one 0/1 count GEMM; Gq as four byte-plane GEMMs (255 * T < 2^31 keeps each plane exact in int32)
+      // G = A_head · A_trT^T as one 0/1 count GEMM; Gq as byte-plane GEMMs (255 * T < 2^31 keeps each plane exact in int32)
       const int n_pad = static_cast<int>(round_up(nr, 128));
       {
         PhaseTimer t(h, MR_T_EXPAND);
@@ -345,7 +374,7 @@ int ensure_head_rows(mr_handle* h) {
       PhaseTimer t(h, MR_T_COUNT);
       int lrc = launch_count_gemm(a_rows, n_pad, h->d_AtrT, h->S, h->pitchT, nr, h->S, EPI_I32, g_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream);
       h->launches++;
-      for (int plane = 0; plane < 4 && !lrc; ++plane) {
+      for (int plane = 0; plane < n_planes && !lrc; ++plane) {
         lrc = launch_count_gemm(a_rows, n_pad, b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->S, h->pitchT, nr, h->S, EPI_ACC_U64,
                                 gq_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream, 8 * plane, plane > 0);
         h->launches++;
@@ -359,9 +388,24 @@ int ensure_head_rows(mr_handle* h) {
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_scatter failed"));
     }
     PhaseTimer t(h, MR_T_PRECOMPUTE);
-    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
+    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->S, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
     h->launches++;
     if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_pack_head_rows failed"));
+  }
+  if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[mrscore] precompute: staged rows %.1f ms\n", ms_since(t_loop)); }
+  if (n_staged < h->n_head) {
+    // direct rows: an L2-sized chunk of final rows at a time
+    long long mb = 48;
+    if (const char* ev = getenv("MRSCORE_DIRECT_CHUNK_MB")) mb = std::max(1LL, atoll(ev));
+    const long long dchunk = std::max<long long>(1, (mb << 20) / (h->spitch * 6));
+    PhaseTimer t(h, MR_T_PRECOMPUTE);
+    for (int r0 = n_staged; r0 < h->n_head; r0 += static_cast<int>(dchunk)) {
+      const int nr = std::min<int>(static_cast<int>(dchunk), h->n_head - r0);
+      int lrc = launch_gram_head_direct(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
+                                        h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, h->stream);
+      h->launches++;
+      if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_direct failed"));
+    }
   }
   // exception list -> CSR by head row (host sort; it is a few thousand entries on MSD-shaped data)
   unsigned int n_ex = 0;
@@ -372,10 +416,11 @@ int ensure_head_rows(mr_handle* h) {
   if (n_ex > ex.capacity) return bail(fail(h, MR_ERR_OOM, "head-row exception list overflowed (%u entries)", n_ex));
   std::vector<int> xr(n_ex), xs(n_ex); std::vector<uint32_t> xg(n_ex); std::vector<unsigned long long> xq(n_ex);
   if (n_ex) {
-    cudaMemcpy(xr.data(), ex.row, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
-    cudaMemcpy(xs.data(), ex.song, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
-    cudaMemcpy(xg.data(), ex.g_extra, n_ex * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    cudaMemcpy(xq.data(), ex.gq_extra, n_ex * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(xr.data(), ex.row, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(xs.data(), ex.song, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(xg.data(), ex.g_extra, n_ex * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(xq.data(), ex.gq_extra, n_ex * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "head-row exception list: %s", cudaGetErrorString(e)));
   }
   free_list(tmp);
   std::vector<unsigned int> order(n_ex);
@@ -385,10 +430,10 @@ int ensure_head_rows(mr_handle* h) {
   std::vector<int> es(n_ex); std::vector<uint32_t> eg(n_ex); std::vector<unsigned long long> eq(n_ex);
   for (unsigned int i = 0; i < n_ex; ++i) { const unsigned int o = order[i]; ex_ptr[xr[o] + 1]++; es[i] = xs[o]; eg[i] = xg[o]; eq[i] = xq[o]; }
   for (int r = 0; r < h->n_head; ++r) ex_ptr[r + 1] += ex_ptr[r];
-  if ((rc = dev_upload(h, &h->d_ex_ptr, ex_ptr.data(), ex_ptr.size(), h->allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_ex_song, es.data(), es.size(), h->allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_ex_g, eg.data(), eg.size(), h->allocs))) return rc;
-  if ((rc = dev_upload(h, &h->d_ex_gq, eq.data(), eq.size(), h->allocs))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_EX_PTR, &h->d_ex_ptr, ex_ptr.data(), ex_ptr.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_EX_SONG, &h->d_ex_song, es.data(), es.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_EX_G, &h->d_ex_g, eg.data(), eg.size()))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_EX_GQ, &h->d_ex_gq, eq.data(), eq.size()))) return rc;
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->n_ex = n_ex;
   if (dbg) fprintf(stderr, "[mrscore] precompute: total %.1f ms\n", ms_since(t_start));
@@ -400,13 +445,15 @@ int ensure_head_rows(mr_handle* h) {
 // panels (two models, 8 bytes per (user, song)) fit in HBM next to the head rows — a large batch shares the row tiles of popular
 // songs among more users (head_rowsum_kernel) — split evenly, plus per batch the balanced work groups of head_rowsum_kernel:
 // segments (Sint row, head-entry range) packed longest-first into n_groups bins of equal total length.
-int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
+constexpr int kPlanTooLarge = -100;   // a work group exceeds the shared-memory staging area: the caller retries with smaller batches
+
+int plan_item_batches_once(mr_handle* h, const std::vector<long long>& hu_ptr, int rows_cap) {
   int rc;
   const int U = h->U;
   h->batch_rows = kUserBatch;
   const size_t panel_rows_have = std::min(h->slot_cap[mr_handle::SL_SINT_U], h->slot_cap[mr_handle::SL_SINT_I]) / (static_cast<size_t>(h->spitch) * 8);
   if (h->space == MR_SPACE_ITEM && static_cast<size_t>(U) <= panel_rows_have && (h->item_batch_cap <= 0 || U <= h->item_batch_cap) &&
-      h->slot_cap[mr_handle::SL_SEL] >= static_cast<size_t>(U) * h->sel_pitch * 8) {
+      (rows_cap <= 0 || U <= rows_cap) && h->slot_cap[mr_handle::SL_SEL] >= static_cast<size_t>(U) * h->sel_pitch * 8) {
     h->batch_rows = std::max(kUserBatch, U);   // the panels of an earlier shard already hold this one as a single batch: no memory query
   } else if (h->space == MR_SPACE_ITEM) {
     size_t free_b = 0, total_b = 0;
@@ -414,10 +461,11 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
     const size_t per_row = static_cast<size_t>(h->spitch) * 16 + static_cast<size_t>(h->sel_pitch) * 8;
     size_t avail = free_b + h->slot_cap[mr_handle::SL_SINT_U] + h->slot_cap[mr_handle::SL_SINT_I] + h->slot_cap[mr_handle::SL_SEL];
     size_t reserve = 6ULL << 30;   // left for the caller's context (torch, NCCL buffers, gathered top-k blocks) and small workspaces
-    if (!h->head_ready) reserve += static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch * 6 + (1ULL << 30);   // head rows + staging come later
+    if (!h->head_ready && h->head_rows_cap == 0) reserve += static_cast<size_t>(std::max(h->n_head, 1)) * h->spitch * 6 + (1ULL << 30);   // head rows + staging come later
     long long max_rows = avail > reserve ? static_cast<long long>((avail - reserve) / per_row) : 0;
     max_rows = std::max<long long>(max_rows, kUserBatch);
     if (h->item_batch_cap > 0) max_rows = std::min<long long>(max_rows, h->item_batch_cap);
+    if (rows_cap > 0) max_rows = std::min<long long>(max_rows, std::max(rows_cap, kUserBatch));
     const int n_batches = static_cast<int>((U + max_rows - 1) / max_rows);
     h->batch_rows = std::max(kUserBatch, (U + n_batches - 1) / n_batches);
   }
@@ -475,8 +523,10 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
     }
   }
   if (ge_size >= (1LL << 31)) return fail(h, MR_ERR_BAD_ARG, "too many head entries in one shard");
-  if (static_cast<size_t>(h->seg_cap) * 16 + static_cast<size_t>(h->ent_cap) * 8 > 48 * 1024)
+  if (static_cast<size_t>(h->seg_cap) * 16 + static_cast<size_t>(h->ent_cap) * 8 > 48 * 1024) {
+    if (h->batch_rows > kUserBatch) return kPlanTooLarge;
     return fail(h, MR_ERR_BAD_ARG, "head_rowsum work group too large for shared-memory staging (%d segments, %d entries)", h->seg_cap, h->ent_cap);
+  }
   if ((rc = slot_upload(h, mr_handle::SL_SEG, &h->d_seg, seg.data(), seg.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_GRP_HDR, &h->d_grp_hdr, grp_hdr.data(), grp_hdr.size()))) return rc;
   int4* d_desc = nullptr;
@@ -489,8 +539,22 @@ int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
   return MR_OK;
 }
 
+// A shard with very many head entries per work group (small S with many users per batch, or few groups) is split into more batches
+// until a group's segments and entries fit the 48 KB staging area of head_rowsum_kernel.
+int plan_item_batches(mr_handle* h, const std::vector<long long>& hu_ptr) {
+  int rows_cap = 0;
+  for (;;) {
+    const int rc = plan_item_batches_once(h, hu_ptr, rows_cap);
+    if (rc != kPlanTooLarge) return rc;
+    rows_cap = std::max(kUserBatch, h->batch_rows / 2);
+  }
+}
+
 enum RunMode { RUN_TOPK, RUN_DENSE, RUN_COUNTS_UBM, RUN_SIM_UBM };
 struct TopkHostOut { int32_t* song; double* score; int32_t* len; };   // RUN_TOPK: caller buffers the finished slices are copied into
+// RUN_DENSE: where the fp64 rows go.  ALL: out[u][s] for every test user (mr_score_dense).  USERS: out[i][s] for the listed users
+// (DIST getRanks1 granularity).  SONGS: d_out[i][u] for the listed songs, gathered on the device (DIST getRanks2 granularity).
+struct DenseOut { enum Kind { ALL, USERS, SONGS } kind; double* out; const int32_t* ids; int n_ids; const int* d_ids; double* d_out; };
 
 int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode mode, void* host_out) {
   const bool need_ubm = model != MODEL_IBM;
@@ -614,8 +678,20 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
         const int cn = std::min(kDenseChunk, nb - c0);
         MR_LAUNCH(h, launch_dense_scores(model, (need_ubm ? h->d_sint_u : h->d_sint_i) + static_cast<long long>(c0) * h->spitch, h->spitch, b0 + c0, cn,
                                          h->S, h->d_rsa, h->d_rsd, h->d_dense, h->stream));
-        MR_CUDA(h, cudaMemcpyAsync(static_cast<double*>(host_out) + static_cast<long long>(b0 + c0) * h->S, h->d_dense,
-                                   static_cast<size_t>(cn) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        const DenseOut* dout = static_cast<const DenseOut*>(host_out);
+        if (dout->kind == DenseOut::ALL) {
+          MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(b0 + c0) * h->S, h->d_dense,
+                                     static_cast<size_t>(cn) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        } else if (dout->kind == DenseOut::USERS) {
+          for (int i = 0; i < dout->n_ids; ++i) {
+            const int r = dout->ids[i] - (b0 + c0);
+            if (r < 0 || r >= cn) continue;
+            MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(i) * h->S, h->d_dense + static_cast<long long>(r) * h->S,
+                                       static_cast<size_t>(h->S) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+          }
+        } else {
+          MR_LAUNCH(h, launch_gather_columns(h->d_dense, cn, h->S, dout->d_ids, dout->n_ids, dout->d_out, h->U, b0 + c0, h->stream));
+        }
         MR_CUDA(h, cudaStreamSynchronize(h->stream));
       }
     } else {
@@ -645,11 +721,11 @@ int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long
   if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
   if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
   if (model == MR_AGG) {
-    if (param < 0 || param > 1) return fail(h, MR_ERR_PARAM_RANGE, "Percentage must be between 0 and 1");   // MR:366-369
+    if (!(param >= 0 && param <= 1)) return fail(h, MR_ERR_PARAM_RANGE, "Percentage must be between 0 and 1");   // MR:366-369 (NaN fails too)
     bp->agg_threshold = static_cast<long long>(param * static_cast<double>(n_total));                        // MR:372 .toInt
   }
   if (model == MR_STOCH) {
-    if (param < 0 || param > 1) return fail(h, MR_ERR_PARAM_RANGE, "Probability must be between 0 and 1");   // MR:434-437
+    if (!(param >= 0 && param <= 1)) return fail(h, MR_ERR_PARAM_RANGE, "Probability must be between 0 and 1");   // MR:434-437
     bp->prob = param; bp->seed = seed;
   }
   return MR_OK;
@@ -695,6 +771,8 @@ void mr_destroy(mr_handle* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->ev_slice) cudaEventDestroy(h->ev_slice);
   for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);
+  if (h->d_g16) cudaFree(h->d_g16);
+  if (h->d_gq32) cudaFree(h->d_gq32);
   free_list(h->allocs);
   if (h->h_carry_seen) cudaFreeHost(h->h_carry_seen);
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
@@ -713,6 +791,12 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if (n_train <= 0 || n_songs <= 0 || n_test < 0 || !deg_train || !deg_song_all) return fail(h, MR_ERR_BAD_ARG, "bad sizes / null degree arrays");
   int rc = check_csr(h, "train", n_train, n_songs, tr_rowptr, tr_col);
   if (rc) return rc;
+  // The fixed-point cosine factors q_k(deg) = rint(2^k / sqrt(deg)) carry a relative rounding error of up to 0.5 * sqrt(deg) / 2^k
+  // (DESIGN.md §3); beyond these degrees it would exceed the 1e-5 the scores are specified to (north_star): refuse instead of degrading.
+  for (int v = 0; v < n_train; ++v)
+    if (deg_train[v] > kMaxDegUbm) return fail(h, MR_ERR_BAD_ARG, "train user %d has %d songs: above %d the 2^24 fixed-point UBM weight leaves the 1e-5 score tolerance", v, deg_train[v], kMaxDegUbm);
+  for (int s = 0; s < n_songs; ++s)
+    if (deg_song_all[s] > kMaxDegIbm) return fail(h, MR_ERR_BAD_ARG, "song %d has %d listeners: above %d the 2^26 fixed-point IBM weight leaves the 1e-5 score tolerance", s, deg_song_all[s], kMaxDegIbm);
   MR_CUDA(h, cudaSetDevice(h->device));
   const int T = n_train, S = n_songs;
   const long long nnz = tr_rowptr[T];
@@ -737,7 +821,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<uint32_t> qv(T), qd(S);
   std::vector<double> rsd(S);
   std::vector<float> rsvf(T), rsdf(S);
-  for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); }
+  for (int v = 0; v < T; ++v) { qv[v] = q_of(deg_train[v], kQScaleUbm); rsvf[v] = rsf_of(deg_train[v]); h->max_qv = std::max(h->max_qv, qv[v]); }
   for (int s = 0; s < S; ++s) { qd[s] = q_of(deg_song_all[s], kQScaleIbm); rsd[s] = rs_of(deg_song_all[s], kQInvIbm); rsdf[s] = rsf_of(deg_song_all[s]); }
   h->song_qsum.assign(S, 0);
   for (int s = 0; s < S; ++s)
@@ -805,7 +889,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
     MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_carry_seen), 4096 * sizeof(unsigned int)));
     memset(h->h_carry_seen, 0, 4096 * sizeof(unsigned int));
   }
-  if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch_cap = std::max(128, atoi(e));
+  if (const char* e = getenv("MRSCORE_ITEM_BATCH")) h->item_batch_cap = std::max(128, atoi(e));   // developer override of MR_OPT_ITEM_BATCH
   if (const char* e = getenv("MRSCORE_HEAD_WORDS_U")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_u = w; }
   if (const char* e = getenv("MRSCORE_HEAD_WORDS_I")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) h->head_words_i = w; }
   if (const char* e = getenv("MRSCORE_HEAD_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) h->head_threads = t; }
@@ -815,6 +899,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
     long long min_deg = std::max<long long>(2, S / 6000);   // below ~64 listeners expanding a song on the fly is cheaper than streaming its row
+    if (h->opt_head_min_deg > 0) min_deg = h->opt_head_min_deg;
     if (const char* e = getenv("MRSCORE_HEAD_MIN_DEG")) min_deg = std::max(1LL, atoll(e));
     size_t free_b = 0, total_b = 0;
     MR_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
@@ -831,6 +916,14 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
       head_song.push_back(s); lst_ptr.push_back(lst_ptr.back() + d);
     }
     h->n_head = static_cast<int>(head_song.size());
+    // rows from n_head_staged on can be built in place: no entry of theirs can overflow 16 / 32 bits (ensure_head_rows)
+    h->n_head_staged = h->n_head;
+    while (h->n_head_staged > 0) {
+      const int s = head_song[h->n_head_staged - 1];
+      if (h->song_qsum[s] >= (1ULL << 32) || csc_ptr[s + 1] - csc_ptr[s] >= 65536) break;
+      --h->n_head_staged;
+    }
+    if (getenv("MRSCORE_PRECOMPUTE_STAGE_ALL")) h->n_head_staged = h->n_head;
     h->song_info.resize(S);
     for (int s = 0; s < S; ++s) h->song_info[s] = {h->head_index[s], h->head_index[s] >= 0 ? qd[s] : static_cast<uint32_t>(h->deg_song_train[s])};
     h->max_qsum = *std::max_element(h->song_qsum.begin(), h->song_qsum.end());
@@ -1079,7 +1172,40 @@ int mr_peer_close(mr_handle* h, void* dev_ptr) {
   return MR_OK;
 }
 
+static int gram_rows_scatter_impl(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld, bool sync);
 int mr_gram_rows_scatter(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld) {
+  return gram_rows_scatter_impl(h, s0, s1, slot_ptrs, n_owners, rows_per_owner, ld, true);
+}
+int mr_gram_rows_scatter_async(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld) {
+  return gram_rows_scatter_impl(h, s0, s1, slot_ptrs, n_owners, rows_per_owner, ld, false);
+}
+
+int mr_peer_signal(mr_handle* h, void* const* flag_ptrs, int n, uint64_t value) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (!flag_ptrs || n < 1 || n > 8) return fail(h, MR_ERR_BAD_ARG, "1..8 flag pointers expected");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  PeerFlags f{};
+  for (int i = 0; i < n; ++i) f.p[i] = static_cast<unsigned long long*>(flag_ptrs[i]);
+  MR_LAUNCH(h, launch_peer_signal(f, n, value, h->stream));
+  return MR_OK;
+}
+
+int mr_peer_wait(mr_handle* h, const void* flags, int n, uint64_t value) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (!flags || n < 1 || n > 8) return fail(h, MR_ERR_BAD_ARG, "1..8 flags expected");
+  MR_CUDA(h, cudaSetDevice(h->device));
+  MR_LAUNCH(h, launch_peer_wait(static_cast<const unsigned long long*>(flags), n, value, h->stream));
+  return MR_OK;
+}
+
+int mr_sync(mr_handle* h) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  MR_CUDA(h, cudaSetDevice(h->device));
+  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MR_OK;
+}
+
+static int gram_rows_scatter_impl(mr_handle* h, int s0, int s1, void* const* slot_ptrs, int n_owners, int rows_per_owner, int64_t ld, bool sync) {
   if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
   if (h->engine != MR_ENGINE_TENSOR) return fail(h, MR_ERR_STATE, "mr_gram_rows_scatter needs the tensor engine (the scatter is the GEMM epilogue)");
   MR_CUDA(h, cudaSetDevice(h->device));
@@ -1108,7 +1234,7 @@ int mr_gram_rows_scatter(mr_handle* h, int s0, int s1, void* const* slot_ptrs, i
   PhaseTimer t(h, MR_T_COUNT);
   MR_LAUNCH(h, launch_count_gemm(h->d_Aj, rows_pad, h->d_AtrT, h->S, h->pitchT, n, h->S, EPI_I32_SCATTER, nullptr, ld, nullptr, nullptr, h->num_sms,
                                  h->stream, 0, 0, slots, n_owners, rows_per_owner));
-  MR_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (sync) MR_CUDA(h, cudaStreamSynchronize(h->stream));
   return MR_OK;
 }
 
@@ -1129,7 +1255,114 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->S))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
-  return run_batches(h, model, bp, 0, RUN_DENSE, out_UxS);
+  DenseOut dout{DenseOut::ALL, out_UxS, nullptr, 0, nullptr, nullptr};
+  return run_batches(h, model, bp, 0, RUN_DENSE, &dout);
+}
+
+static int score_subset(mr_handle* h, int model, const int32_t* ids, int n, double* out, bool songs) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "model must be MR_UBM or MR_IBM");
+  if (n < 0 || (n > 0 && (!ids || !out))) return fail(h, MR_ERR_BAD_ARG, "null id list / output");
+  const int limit = songs ? h->S : h->U;
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= limit) return fail(h, MR_ERR_BAD_ARG, "%s id %d out of range [0,%d)", songs ? "song" : "test user", ids[i], limit);
+  if (n == 0) return MR_OK;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->S))) return rc;
+  if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
+  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
+  std::vector<void*> tmp;
+  DenseOut dout{songs ? DenseOut::SONGS : DenseOut::USERS, out, ids, n, nullptr, nullptr};
+  if (songs) {
+    int* d_ids = nullptr;
+    if ((rc = dev_upload(h, &d_ids, ids, static_cast<size_t>(n), tmp)) || (rc = dev_alloc(h, &dout.d_out, static_cast<size_t>(n) * h->U, tmp))) { free_list(tmp); return rc; }
+    dout.d_ids = d_ids;
+  }
+  rc = run_batches(h, model, bp, 0, RUN_DENSE, &dout);
+  if (!rc && songs) {
+    cudaError_t e = cudaMemcpyAsync(out, dout.d_out, static_cast<size_t>(n) * h->U * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(h, MR_ERR_CUDA, "mr_score_songs copy-out: %s", cudaGetErrorString(e));
+  }
+  free_list(tmp);
+  return rc;
+}
+
+int mr_score_users(mr_handle* h, int model, const int32_t* user_idx, int n, double* out_nxS) { return score_subset(h, model, user_idx, n, out_nxS, false); }
+int mr_score_songs(mr_handle* h, int model, const int32_t* song_ids, int n, double* out_nxU) { return score_subset(h, model, song_ids, n, out_nxU, true); }
+
+int mr_map_at_k(mr_handle* h, int k, const int32_t* top_song, const int32_t* top_len, int n_users, const int64_t* lab_rowptr, const int32_t* lab_col,
+                double* out_map, double* out_ap) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (k < 1 || n_users <= 0 || !lab_rowptr || !out_map) return fail(h, MR_ERR_BAD_ARG, "null / empty arguments");
+  if ((top_song == nullptr) != (top_len == nullptr)) return fail(h, MR_ERR_BAD_ARG, "top_song and top_len must both be given or both be null");
+  const long long n_lab = lab_rowptr[n_users];
+  if (lab_rowptr[0] != 0 || n_lab < 0 || (n_lab > 0 && !lab_col)) return fail(h, MR_ERR_BAD_ARG, "bad label CSR");
+  for (int u = 0; u < n_users; ++u) {
+    if (lab_rowptr[u + 1] < lab_rowptr[u]) return fail(h, MR_ERR_BAD_ARG, "label rowptr not monotone at row %d", u);
+    for (long long i = lab_rowptr[u] + 1; i < lab_rowptr[u + 1]; ++i)
+      if (lab_col[i] <= lab_col[i - 1]) return fail(h, MR_ERR_BAD_ARG, "label row %d not ascending/unique", u);
+  }
+  MR_CUDA(h, cudaSetDevice(h->device));
+  const int* d_song = nullptr; const int* d_len = nullptr;
+  std::vector<void*> tmp;
+  int rc;
+  if (!top_song) {   // rank the device-resident result of the last mr_topk_device / mr_topk
+    if (!h->have_topk || h->out_k != k || n_users != h->U) return fail(h, MR_ERR_STATE, "no top-%d result of %d users on the device", k, n_users);
+    d_song = h->d_out_song; d_len = h->d_out_len;
+  } else {
+    int *ds = nullptr, *dl = nullptr;
+    if ((rc = dev_upload(h, &ds, top_song, static_cast<size_t>(n_users) * k, tmp)) || (rc = dev_upload(h, &dl, top_len, static_cast<size_t>(n_users), tmp))) { free_list(tmp); return rc; }
+    d_song = ds; d_len = dl;
+  }
+  std::vector<long long> lp(lab_rowptr, lab_rowptr + n_users + 1);
+  long long* d_lp = nullptr; int* d_lc = nullptr; double* d_ap = nullptr;
+  if ((rc = dev_upload(h, &d_lp, lp.data(), lp.size(), tmp)) || (rc = dev_upload(h, &d_lc, lab_col, static_cast<size_t>(n_lab), tmp)) ||
+      (rc = dev_alloc(h, &d_ap, static_cast<size_t>(n_users), tmp))) { free_list(tmp); return rc; }
+  int lrc;
+  {
+    PhaseTimer t(h, MR_T_OTHER);
+    lrc = launch_map_at_k(d_song, d_len, n_users, k, d_lp, d_lc, d_ap, h->stream);
+    h->launches++;
+  }
+  std::vector<double> ap(n_users);
+  cudaError_t e = lrc ? cudaErrorLaunchFailure : cudaMemcpyAsync(ap.data(), d_ap, static_cast<size_t>(n_users) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  free_list(tmp);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_map_at_k: %s", cudaGetErrorString(e));
+  double total = 0.0; long long n_eval = 0;
+  for (int u = 0; u < n_users; ++u) {
+    if (lab_rowptr[u + 1] > lab_rowptr[u]) { total += ap[u]; ++n_eval; }   // left fold in ascending user order, users without labels skipped
+    if (out_ap) out_ap[u] = ap[u];
+  }
+  *out_map = n_eval > 0 ? total / static_cast<double>(n_eval) : 0.0;
+  return MR_OK;
+}
+
+int mr_set_option(mr_handle* h, int option, int64_t value) {
+  if (!h) return MR_ERR_STATE;
+  switch (option) {
+    case MR_OPT_HEAD_MIN_DEG:
+      if (h->loaded) return fail(h, MR_ERR_STATE, "MR_OPT_HEAD_MIN_DEG must be set before mr_load (it selects the head songs)");
+      if (value < 0) return fail(h, MR_ERR_BAD_ARG, "MR_OPT_HEAD_MIN_DEG must be >= 0");
+      h->opt_head_min_deg = value;
+      return MR_OK;
+    case MR_OPT_ITEM_BATCH:
+      if (value < 0) return fail(h, MR_ERR_BAD_ARG, "MR_OPT_ITEM_BATCH must be >= 0");
+      h->item_batch_cap = value > 0 ? static_cast<int>(std::max<int64_t>(128, std::min<int64_t>(value, 1 << 30))) : 0;
+      return MR_OK;
+    default:
+      return fail(h, MR_ERR_BAD_ARG, "unknown option %d", option);
+  }
+}
+
+int mr_invalidate_prepared(mr_handle* h) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_invalidate_prepared: %s", cudaGetErrorString(e));
+  h->head_ready = false; h->n_ex = 0;
+  return MR_OK;
 }
 
 int mr_blend_dense(mr_handle* h, int kind, double param, uint64_t seed, const double* ubm, const double* ibm, double* out,
@@ -1203,12 +1436,24 @@ static int topk_impl(mr_handle* h, int model, double param, uint64_t seed, int k
   int rc = require_test(h);
   if (rc) return rc;
   if (k < 1 || k > 1024) return fail(h, MR_ERR_BAD_ARG, "k must be in [1,1024], got %d", k);
+  // The select ranks IEEE bit patterns of non-negative scores.  The reference's linear combination accepts any alpha (MR:317-330 has
+  // no range check) and mr_blend_dense follows it, but outside [0,1] a blended score can be negative, which has no place in a ranking
+  // of cosine sums: getTopK rejects it (documented deviation).
+  if (model == MR_LC && !(param >= 0 && param <= 1))
+    return fail(h, MR_ERR_PARAM_RANGE, "getTopK: alpha of the linear combination must be between 0 and 1");
   BlendParams bp;
   if ((rc = make_blend_params(h, model, param, seed, h->n_pairs_total, &bp))) return rc;
   bp.pair_base = h->d_pair_base;
-  if ((rc = slot_alloc(h, mr_handle::SL_OUT_SONG, &h->d_out_song, static_cast<size_t>(h->U) * k))) return rc;
-  if ((rc = slot_alloc(h, mr_handle::SL_OUT_SCORE, &h->d_out_score, static_cast<size_t>(h->U) * k))) return rc;
-  if ((rc = slot_alloc(h, mr_handle::SL_OUT_LEN, &h->d_out_len, static_cast<size_t>(h->U)))) return rc;
+  {  // one packed block (song | score | len) so that a caller can ship the whole result with a single transfer (mr_topk_packed)
+    const size_t song_b = static_cast<size_t>(round_up(static_cast<long long>(h->U) * k * 4, 16)), score_b = static_cast<size_t>(h->U) * k * 8,
+                 len_b = static_cast<size_t>(round_up(static_cast<long long>(h->U) * 4, 16));
+    char* base = nullptr;
+    if ((rc = slot_alloc(h, mr_handle::SL_OUT_PACK, &base, song_b + score_b + len_b))) return rc;
+    h->d_out_song = reinterpret_cast<int*>(base);
+    h->d_out_score = reinterpret_cast<double*>(base + song_b);
+    h->d_out_len = reinterpret_cast<int*>(base + song_b + score_b);
+    h->out_pack_bytes = song_b + score_b + len_b;
+  }
   h->out_k = k;
   if (model != MR_UBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
   h->have_topk = false;
@@ -1243,6 +1488,17 @@ int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** l
   if (song) *song = h->d_out_song;
   if (score) *score = h->d_out_score;
   if (len) *len = h->d_out_len;
+  return MR_OK;
+}
+
+int mr_topk_packed(mr_handle* h, int k, void** base, uint64_t* bytes, uint64_t* score_offset, uint64_t* len_offset) {
+  int rc = require_test(h);
+  if (rc) return rc;
+  if (!h->have_topk || h->out_k != k) return fail(h, MR_ERR_STATE, "no top-%d result on the device (call mr_topk_device first)", k);
+  if (base) *base = h->d_out_song;
+  if (bytes) *bytes = h->out_pack_bytes;
+  if (score_offset) *score_offset = static_cast<uint64_t>(reinterpret_cast<char*>(h->d_out_score) - reinterpret_cast<char*>(h->d_out_song));
+  if (len_offset) *len_offset = static_cast<uint64_t>(reinterpret_cast<char*>(h->d_out_len) - reinterpret_cast<char*>(h->d_out_song));
   return MR_OK;
 }
 

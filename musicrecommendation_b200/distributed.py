@@ -73,6 +73,36 @@ def gather_topk(song, score, length, n_users_total: int, world: int, rank: int, 
     return tuple(outs)
 
 
+_PACKED: dict = {}
+
+
+def gather_topk_packed(mr, k: int, world: int, rank: int, lib_stream, comm_stream, dst: int = 0):
+    """The reference's `.collect` (distributed.scala:451-452: results go to the driver only) as ONE NCCL gather of the packed
+    (song | score | len) block of every rank's shard to rank `dst`, issued on `comm_stream` so that it overlaps whatever the handle
+    computes next.  The block is first copied device-to-device into a staging tensor (the library reuses its result block for the
+    next model); the library stream waits for that copy, nothing waits for the gather until the caller joins comm_stream.
+    Returns the list of per-rank uint8 blocks on rank dst (None elsewhere); equal shard sizes are required (pad the shards otherwise)."""
+    import torch
+    import torch.distributed as dist
+    block, _, _ = mr.topk_packed_tensor(k)
+    key = (block.numel(), world, rank)
+    st = _PACKED.get(key)
+    if st is None:
+        recv = [[torch.empty(block.numel(), dtype=torch.uint8, device=block.device) for _ in range(world)] for _ in range(2)] if rank == dst else None
+        st = _PACKED[key] = {"stage": torch.empty_like(block), "recv": recv, "turn": 0, "copied": torch.cuda.Event()}
+    comm_stream.wait_stream(lib_stream)
+    with torch.cuda.stream(comm_stream):
+        st["stage"].copy_(block, non_blocking=True)
+        st["copied"].record(comm_stream)
+        bufs = None
+        if rank == dst:
+            bufs = st["recv"][st["turn"]]
+            st["turn"] ^= 1
+        dist.gather(st["stage"], gather_list=bufs, dst=dst)
+    lib_stream.wait_event(st["copied"])
+    return bufs
+
+
 def split_train_users(ds: Dataset, rank: int, world: int) -> Dataset:
     """K-split of the item-item Gram (BASELINE configs[4]): rank r keeps the train users of its contiguous range, every song.
     deg_song stays global — the cosine denominators count all listeners (MR:237)."""

@@ -174,7 +174,8 @@ class MusicRecommender:
     """`new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12).  Also accepts a ready `Dataset`."""
 
     def __init__(self, trainFile, testFile=None, testLabelsFile=None, device: int = 0, engine: int = _lib.MR_ENGINE_AUTO,
-                 profile: bool = False, space: int = _lib.MR_SPACE_AUTO, ingest: str = "host"):
+                 profile: bool = False, space: int = _lib.MR_SPACE_AUTO, ingest: str = "host", head_min_deg: int = 0,
+                 item_batch: int = 0):
         if isinstance(trainFile, Dataset):
             ds = trainFile
         elif ingest == "native":
@@ -189,6 +190,10 @@ class MusicRecommender:
         dev = (C.c_int * 1)(device)
         rc = self._lib.mr_create(C.byref(self._h), dev, 1, engine | space | (_lib.MR_PROFILE if profile else 0))
         self._check(rc)
+        if head_min_deg:
+            self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_HEAD_MIN_DEG, int(head_min_deg)))
+        if item_batch:
+            self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_ITEM_BATCH, int(item_batch)))
         a = self._arrs = dict(
             tr_ptr=np.ascontiguousarray(ds.tr_ptr, np.int64), tr_col=np.ascontiguousarray(ds.tr_col, np.int32),
             te_ptr=np.ascontiguousarray(ds.te_ptr, np.int64), te_col=np.ascontiguousarray(ds.te_col, np.int32),
@@ -298,6 +303,40 @@ class MusicRecommender:
         """Build the item-space head rows now (one-off per train set) instead of lazily."""
         self._check(self._lib.mr_prepare(self._h))
 
+    def invalidate_prepared(self):
+        """Forget the head rows so that the next prepare() / scoring call rebuilds them (bench.py: the whole model build inside a step)."""
+        self._check(self._lib.mr_invalidate_prepared(self._h))
+
+    def getRanks1(self, model: int, users) -> np.ndarray:
+        """DIST UserBasedModel/ItemBasedModel.getRanks1(user) (DIST:198-205, 269-276) for the listed test users of the current shard:
+        [len(users), S] fp64, NaN at listened pairs."""
+        ids = np.ascontiguousarray(users, np.int32)
+        out = np.empty((len(ids), self.ds.S), np.float64)
+        self._check(self._lib.mr_score_users(self._h, model, _p(ids), len(ids), _p(out)))
+        return out
+
+    def getRanks2(self, model: int, songs) -> np.ndarray:
+        """DIST getRanks2(song) (DIST:214-221, 285-292) for the listed songs: [len(songs), U] fp64, NaN where the user listened."""
+        ids = np.ascontiguousarray(songs, np.int32)
+        out = np.empty((len(ids), self.ds.U), np.float64)
+        self._check(self._lib.mr_score_songs(self._h, model, _p(ids), len(ids), _p(out)))
+        return out
+
+    def mapAtK(self, k: int = 500, top=None, per_user: bool = False):
+        """mAP@k (north_star's mAP@500; MSD-challenge definition, include/mrscore.h) of ranked lists against this data set's label rows.
+        top = (song [U,k], len [U]) as getTopK returns them, or None for the device-resident result of the last getTopK / mr_topk_device."""
+        lp = np.ascontiguousarray(self.ds.lab_ptr, np.int64)
+        lc = np.ascontiguousarray(self.ds.lab_col, np.int32)
+        out = C.c_double(0.0)
+        ap = np.zeros(self.ds.U, np.float64)
+        if top is None:
+            self._check(self._lib.mr_map_at_k(self._h, k, None, None, self.ds.U, _p(lp), _p(lc), C.byref(out), _p(ap)))
+        else:
+            song = np.ascontiguousarray(top[0], np.int32)
+            ln = np.ascontiguousarray(top[1], np.int32)
+            self._check(self._lib.mr_map_at_k(self._h, song.shape[1], _p(song), _p(ln), song.shape[0], _p(lp), _p(lc), C.byref(out), _p(ap)))
+        return (float(out.value), ap) if per_user else float(out.value)
+
     def topk_device_tensors(self, k: int):
         """torch views (no copy) of the last mr_topk_device result in this GPU's HBM: (song int32 [U,k], score f64 [U,k], len int32 [U])."""
         import torch
@@ -310,6 +349,17 @@ class MusicRecommender:
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
         return (torch.as_tensor(_Arr(ps.value, (U, k), "<i4"), device="cuda"), torch.as_tensor(_Arr(pv.value, (U, k), "<f8"), device="cuda"),
                 torch.as_tensor(_Arr(pl.value, (U,), "<i4"), device="cuda"))
+
+    def topk_packed_tensor(self, k: int):
+        """The last top-k result as ONE uint8 torch view of device memory plus the byte offsets of its parts:
+        (block, score_offset, len_offset); song int32 [U,k] starts at 0."""
+        import torch
+        base, nbytes, so, lo = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.mr_topk_packed(self._h, k, C.byref(base), C.byref(nbytes), C.byref(so), C.byref(lo)))
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (int(nbytes.value),), "typestr": "|u1", "data": (base.value, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda"), int(so.value), int(lo.value)
 
     # ------------------------------------------------------------------ parity probes / similarity products
     def counts_ubm(self) -> np.ndarray:
@@ -349,9 +399,20 @@ class MusicRecommender:
     def peer_close(self, ptr: int):
         self._check(self._lib.mr_peer_close(self._h, C.c_void_p(ptr)))
 
-    def gram_rows_scatter(self, s0: int, s1: int, slot_ptrs, rows_per_owner: int, ld: int):
+    def gram_rows_scatter(self, s0: int, s1: int, slot_ptrs, rows_per_owner: int, ld: int, sync: bool = True):
         arr = (C.c_void_p * len(slot_ptrs))(*slot_ptrs)
-        self._check(self._lib.mr_gram_rows_scatter(self._h, s0, s1, arr, len(slot_ptrs), rows_per_owner, ld))
+        fn = self._lib.mr_gram_rows_scatter if sync else self._lib.mr_gram_rows_scatter_async
+        self._check(fn(self._h, s0, s1, arr, len(slot_ptrs), rows_per_owner, ld))
+
+    def peer_signal(self, flag_ptrs, value: int):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._check(self._lib.mr_peer_signal(self._h, arr, len(flag_ptrs), value))
+
+    def peer_wait(self, flags_ptr: int, n: int, value: int):
+        self._check(self._lib.mr_peer_wait(self._h, C.c_void_p(flags_ptr), n, value))
+
+    def sync(self):
+        self._check(self._lib.mr_sync(self._h))
 
     def similarity_ubm(self) -> np.ndarray:
         out = np.empty((self.ds.U, self.ds.T), np.float32)
@@ -377,25 +438,14 @@ class MusicRecommender:
                          "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users"], list(v)))
 
     # ------------------------------------------------------------------ model file I/O (MR:489-512)
-    def writeModelOnFile(self, model: Model, outputFileName: str = "") -> None:
-        """`user \\t song \\t Double.toString(score) \\n` per element, in model order (MR:492-494)."""
-        with open(outputFileName, "w", encoding="utf-8", newline="") as out:
-            buf = io.StringIO()
-            for user, (song, score) in model.tuples():
-                buf.write(f"{user}\t{song}\t{double_to_string(score)}\n")
-            out.write(buf.getvalue())
+    def writeModelOnFile(self, model: Model, outputFileName: str = "") -> int:
+        """`user \\t song \\t Double.toString(score) \\n` per element, in model order (MR:492-494), through the native writer
+        `mr_write_model` (csrc/modelio.cu).  Returns the number of lines written."""
+        return write_model_file(model, outputFileName, self._lib)
 
     def importModelFromFile(self, pathToModel: str):
         """Array[(String, String, Double)] sorted by (user, song, score desc) (MR:505-512)."""
-        rows = []
-        with open(pathToModel, "r", encoding="utf-8") as f:
-            for line in f:
-                parts = line.rstrip("\n").split("\t")
-                if len(parts) != 3:
-                    raise ValueError(f"scala.MatchError: {line!r}")
-                rows.append((parts[0], parts[1], float(parts[2])))
-        rows.sort(key=lambda r: (r[0], r[1], -r[2]))
-        return rows
+        return import_model_file(pathToModel)
 
     # ------------------------------------------------------------------ evaluation (MR:521-639), host-side like the reference
     def evaluateModel(self, model: Model, parallel: bool = False, n_thresholds: int = 10) -> float:
@@ -407,6 +457,51 @@ class MusicRecommender:
         out = C.c_double(0.0)
         self._check(self._lib.mr_evaluate_dense(self._h, _p(sc), sc.shape[0], sc.shape[1], _p(lp), _p(lc), n_thresholds, C.byref(out)))
         return float(out.value)
+
+
+def _string_table(names, n):
+    """id -> string list as (uint8 chars, int64 offsets [n+1]); ints stand in for missing tables."""
+    enc = [(str(i) if names is None else names[i]).encode("utf-8") for i in range(n)]
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([len(b) for b in enc], out=off[1:])
+    chars = np.frombuffer(b"".join(enc) or b"\0", np.uint8)
+    return np.ascontiguousarray(chars), off
+
+
+def write_model_file(model: Model, path: str, lib=None) -> int:
+    """writeModelOnFile (MR:489-496) natively: one `user\\tsong\\tDouble.toString(score)\\n` line per emitted pair."""
+    lib = lib or _lib.load()
+    sc = np.ascontiguousarray(model.scores, np.float64)
+    U, S = sc.shape
+    uc, uo = _string_table(model.test_users, U)
+    scs, so = _string_table(model.songs, S)
+    rows = C.c_int64(0)
+    rc = lib.mr_write_model(str(path).encode(), _p(sc), U, S, _p(uc), _p(uo), _p(scs), _p(so), 0, C.byref(rows))
+    if rc != _lib.MR_OK:
+        raise OSError(f"mr_write_model({path!r}) failed with code {rc}")
+    return int(rows.value)
+
+
+def write_model_file_py(model: Model, path: str) -> None:
+    """The same file from pure Python (javafmt.double_to_string): the independent check of the native formatter in tests."""
+    with open(path, "w", encoding="utf-8", newline="") as out:
+        buf = io.StringIO()
+        for user, (song, score) in model.tuples():
+            buf.write(f"{user}\t{song}\t{double_to_string(score)}\n")
+        out.write(buf.getvalue())
+
+
+def import_model_file(path: str):
+    """importModelFromFile (MR:505-512): Array[(String, String, Double)] sorted by (user, song, score desc)."""
+    rows = []
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f:
+            parts = line.rstrip("\n").split("\t")
+            if len(parts) != 3:
+                raise ValueError(f"scala.MatchError: {line!r}")
+            rows.append((parts[0], parts[1], float(parts[2])))
+    rows.sort(key=lambda r: (r[0], r[1], -r[2]))
+    return rows
 
 
 def evaluate_map(scores: np.ndarray, ds: Dataset, n_thresholds: int = 10) -> float:

@@ -64,6 +64,7 @@ def lib():
         _lib.mro_round_at.restype = C.c_double
         _lib.mro_round_at.argtypes = [C.c_int, C.c_double]
         _lib.mro_blend.restype = C.c_int
+        _lib.mro_map_at_k.restype = C.c_double
     return _lib
 
 
@@ -86,6 +87,11 @@ def num_threads() -> int:
 
 def set_threads(n: int) -> None:
     os.environ["OMP_NUM_THREADS"] = str(n)
+
+
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun exports 1) for every later call."""
+    lib().mro_set_num_threads(C.c_int(int(n)))
 
 
 def q(deg: int, model: int = UBM) -> int:
@@ -140,6 +146,28 @@ def canon_scores(ds, model: int, u0: int = 0, u1: int | None = None) -> np.ndarr
     out = np.empty((u1 - u0, ds.S), np.float64)
     lib().mro_canon_scores(C.byref(d), C.c_int(model), C.c_int32(u0), C.c_int32(u1), _p(out))
     return out
+
+
+def fp64_scores(ds, model: int, u0: int = 0, u1: int | None = None) -> np.ndarray:
+    """The reference's fp64 terms c/(sqrt(a)*sqrt(b)) summed in ascending-id order through the inverted index (no fixed point):
+    the third restatement, used by the ranking differential test.  Dense [u1-u0, S], NaN at listened pairs."""
+    d, keep = _data(ds)
+    u1 = ds.U if u1 is None else u1
+    out = np.empty((u1 - u0, ds.S), np.float64)
+    lib().mro_fp64_scores(C.byref(d), C.c_int(model), C.c_int32(u0), C.c_int32(u1), _p(out))
+    return out
+
+
+def map_at_k(top_song: np.ndarray, top_len: np.ndarray, ds, per_user: bool = False):
+    """MSD-challenge mAP@k of ranked lists [U,k] against the label CSR of ds (definition in mr_oracle.c)."""
+    top_song = np.ascontiguousarray(top_song, np.int32)
+    top_len = np.ascontiguousarray(top_len, np.int32)
+    U, k = top_song.shape
+    lab_ptr = np.ascontiguousarray(ds.lab_ptr, np.int64)
+    lab_col = np.ascontiguousarray(ds.lab_col, np.int32)
+    ap = np.zeros(U, np.float64)
+    m = float(lib().mro_map_at_k(_p(top_song), _p(top_len), C.c_int32(U), C.c_int32(k), _p(lab_ptr), _p(lab_col), _p(ap)))
+    return (m, ap) if per_user else m
 
 
 def blend(kind: int, param: float, ubm: np.ndarray, ibm: np.ndarray, seed: int = 0, first_index: int = 0,

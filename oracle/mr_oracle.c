@@ -85,6 +85,15 @@ MRO_API int mro_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU legs of bench.py set the thread count explicitly. */
+MRO_API void mro_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* song -> listeners map over train AND test-visible users (MR:41, 53, 60-62); train users are
  * numbered 0..T-1, test users T..T+U-1.  Returned arrays are malloc'ed. */
 static void build_song_to_users(const mro_data *d, int64_t **ptr_out, int32_t **usr_out) {
@@ -429,4 +438,96 @@ MRO_API double mro_evaluate(const double *scores, int32_t U, int32_t S, const in
 MRO_API double mro_round_at(int p, double x) {
   double s = pow(10.0, p);
   return (double)llround(floor(x * s + 0.5)) / s; /* Math.round(double) = floor(x + 0.5) */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FP64 restatement on the CSR — the reference's expressions, summed in ascending-id order     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* A third, independent restatement used only by the ranking differential test: the reference's own fp64
+ * terms  c / (sqrt(a) * sqrt(b))  (MR:147-148, 237-238) summed left to right with trainUsers / songs in
+ * ascending id order (MR:166, 257 sum in HashSet order), computed through the inverted index
+ * instead of linear `contains` scans so that it is feasible on an MSD-shaped shard.  No fixed point
+ * anywhere: it shows that ranking the canonical integers ranks the reference's doubles.
+ * out[(u-u0)][S] fp64, NaN at listened pairs. */
+MRO_API void mro_fp64_scores(const mro_data *d, int model, int32_t u0, int32_t u1, double *out) {
+  int64_t *cp; int32_t *cu; build_train_csc(d, &cp, &cu);
+  int64_t S = d->S;
+#pragma omp parallel
+  {
+    int32_t *cnt = (int32_t *)calloc((size_t)((d->T > S ? d->T : S) + 1), sizeof(int32_t));
+    int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)((d->T > S ? d->T : S) + 1));
+#pragma omp for schedule(dynamic, 1)
+    for (int32_t u = u0; u < u1; ++u) {
+      double *row = out + (int64_t)(u - u0) * S;
+      for (int64_t s = 0; s < S; ++s) row[s] = 0.0;
+      if (model == 0) {
+        /* cnt[v] = |I_u ∩ I_v| (MR:142-145); then for v ascending: row[s] += cnt / (sqrt|I_u| * sqrt|I_v|) for s in I_v (MR:161-166) */
+        for (int64_t i = d->te_ptr[u]; i < d->te_ptr[u + 1]; ++i) {
+          int32_t j = d->te_col[i];
+          for (int64_t k = cp[j]; k < cp[j + 1]; ++k) cnt[cu[k]]++;
+        }
+        for (int32_t v = 0; v < d->T; ++v) if (cnt[v]) {
+          double denominator = sqrt((double)d->deg_te[u]) * sqrt((double)d->deg_tr[v]);
+          double w = denominator != 0 ? cnt[v] / denominator : 0.0;
+          for (int64_t m = d->tr_ptr[v]; m < d->tr_ptr[v + 1]; ++m) row[d->tr_col[m]] += w;
+          cnt[v] = 0;
+        }
+      } else {
+        /* for s2 = j in I_u ascending (MR:251-253): cnt[s] = |U_s ∩ U_j| over train users (MR:232-235); row[s] += cnt / (sqrt d_s * sqrt d_j) */
+        for (int64_t i = d->te_ptr[u]; i < d->te_ptr[u + 1]; ++i) {
+          int32_t j = d->te_col[i]; int32_t nt = 0;
+          for (int64_t k = cp[j]; k < cp[j + 1]; ++k) {
+            int32_t v = cu[k];
+            for (int64_t m = d->tr_ptr[v]; m < d->tr_ptr[v + 1]; ++m) { int32_t s = d->tr_col[m]; if (cnt[s]++ == 0) touched[nt++] = s; }
+          }
+          for (int32_t t = 0; t < nt; ++t) {
+            int32_t s = touched[t];
+            if (s != j) {
+              double denominator = sqrt((double)d->deg_song[s]) * sqrt((double)d->deg_song[j]);
+              row[s] += denominator != 0 ? cnt[s] / denominator : 0;
+            }
+            cnt[s] = 0;
+          }
+        }
+      }
+      for (int64_t i = d->te_ptr[u]; i < d->te_ptr[u + 1]; ++i) row[d->te_col[i]] = NAN;
+    }
+    free(cnt); free(touched);
+  }
+  free(cp); free(cu);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* mAP@k on the ranked lists — new derived metric (north_star "mAP@500")  */
+/* ------------------------------------------------------------------------------------------ */
+
+/* The reference has no ranking and therefore no mAP@k (its "mAP" is the threshold sweep above, MR:588-627).
+ * Definition used here = the Million Song Dataset Challenge's truncated mAP: for test user u with hidden
+ * (label) songs L_u and ranked recommendations r_1..r_n (n = top_len[u] <= k, listened songs never appear):
+ *     AP@k(u) = ( sum_{i=1..n} [r_i in L_u] * hits_i / i ) / min(|L_u|, k),   hits_i = #{t <= i : r_t in L_u}
+ * and mAP@k = mean of AP@k over the test users that have at least one label row (users without labels are
+ * skipped, as a user without hidden songs has no defined precision).  Terms are added in rank order, users
+ * in ascending id order (both fp64, left folds) — the GPU kernel does the same, so results are bit-identical.
+ * Label rows are ascending/unique; ap_out (optional) receives the per-user AP (0 for users without labels). */
+MRO_API double mro_map_at_k(const int32_t *top_song, const int32_t *top_len, int32_t U, int32_t k, const int64_t *lab_ptr,
+                            const int32_t *lab_col, double *ap_out) {
+  double total = 0.0; int64_t n_eval = 0;
+  for (int32_t u = 0; u < U; ++u) {
+    const int32_t *lab = lab_col + lab_ptr[u]; int64_t nl = lab_ptr[u + 1] - lab_ptr[u];
+    double ap = 0.0;
+    if (nl > 0) {
+      int32_t hits = 0; int32_t n = top_len[u] < k ? top_len[u] : k;
+      for (int32_t i = 0; i < n; ++i) {
+        int32_t s = top_song[(int64_t)u * k + i];
+        int64_t lo = 0, hi = nl;
+        while (lo < hi) { int64_t m = (lo + hi) >> 1; if (lab[m] < s) lo = m + 1; else hi = m; }
+        if (lo < nl && lab[lo] == s) { hits++; ap += (double)hits / (double)(i + 1); }
+      }
+      ap = ap / (double)(nl < k ? nl : k);
+      total += ap; n_eval++;
+    }
+    if (ap_out) ap_out[u] = ap;
+  }
+  return n_eval > 0 ? total / (double)n_eval : 0.0;
 }

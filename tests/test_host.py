@@ -132,3 +132,43 @@ def test_header_is_plain_c_and_the_library_links_from_c(mrlib, tmp_path):
         assert "user 0  #1" in r.stdout
     else:
         assert r.returncode == _lib.MR_ERR_CUDA and "no CPU fallback" in r.stderr
+
+
+def test_native_double_formatter_is_java_double_to_string(mrlib):
+    """mr_format_double (csrc/modelio.cu, std::to_chars digits + Java's layout rules) against the independent Python formatter."""
+    buf = C.create_string_buffer(40)
+    rng = np.random.default_rng(7)
+    vals = list(rng.random(3000) * 10) + list(10.0 ** rng.uniform(-15, 15, 3000)) + [0.0, 1.0, 1e7, 1e-3, 9999999.999, 0.00099999999, 123.0,
+                                                                                      5e-324, 1.7976931348623157e308, 0.4999999999999999, 2.0 ** 53, 1e22, 1e23]
+    for x in vals:
+        n = mrlib.mr_format_double(float(x), buf)
+        assert buf.value.decode() == double_to_string(float(x)) and n == len(buf.value)
+        assert float(buf.value) == float(x)                      # `.toDouble` in importModelFromFile gets the same bits back (MR:509)
+
+
+def test_model_file_round_trip(mrlib, oracle_lib, tmp_path):
+    """writeModelOnFile -> importModelFromFile (MR:489-512) on real score arrays: every emitted pair comes back with the same bits, in
+    (user, song) order, listened pairs absent; the native writer's bytes equal the pure-Python writer's."""
+    ds = synth(T=120, U=9, S=900, seed=13)
+    users = [f"{i:040x}" for i in range(ds.U)]
+    songs = ["SO" + f"{i:016X}" for i in range(ds.S)]
+    for m in (oracle_lib.UBM, oracle_lib.IBM):
+        scores = oracle_lib.canon_scores(ds, m)
+        model = recommender.Model(scores, users, songs, "m")
+        p_native, p_py = tmp_path / f"native_{m}.txt", tmp_path / f"py_{m}.txt"
+        rows = recommender.write_model_file(model, str(p_native), mrlib)
+        recommender.write_model_file_py(model, str(p_py))
+        assert rows == ds.n_pairs == len(model)
+        assert p_native.read_bytes() == p_py.read_bytes()
+        back = recommender.import_model_file(str(p_native))
+        assert len(back) == ds.n_pairs
+        want = list(model.tuples())
+        assert [(u, s) for u, s, _ in back] == [(u, s) for u, (s, _) in want]         # ids are zero-padded: string order == id order
+        np.testing.assert_array_equal(np.array([v for _, _, v in back]).view(np.int64), np.array([v for _, (_, v) in want]).view(np.int64))
+    # the hand-derived fixture: the score that is NOT 0.5 keeps all its digits
+    fx = fixture_4_3()
+    model = recommender.Model(oracle_lib.naive_scores(fx, oracle_lib.UBM), fx.test_users, fx.songs, "ubm")
+    p = tmp_path / "fx.txt"
+    recommender.write_model_file(model, str(p), mrlib)
+    assert p.read_text().splitlines()[0] == "X\ts2\t0.4999999999999999"
+    assert p.read_text().splitlines()[1] == "X\ts3\t0.0"

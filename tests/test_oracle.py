@@ -169,3 +169,86 @@ def test_synth_shapes():
         assert not (vis & lab)
     again = synth_config("c1")
     np.testing.assert_array_equal(again.tr_col, synth_config("c1").tr_col)
+
+
+def ranking_differential(oracle_lib, ds, k, u0=0, u1=None):
+    """Canonical (fixed-point) ranking against the ranking of the reference's own fp64 scores (oracle.fp64_scores: c/(sqrt a * sqrt b)
+    terms summed in ascending-id order, no fixed point).  Returns (max relative score error, inversions, missed members) where an
+    inversion / a miss only counts when the fp64 scores involved differ by more than 1e-12 relative (closer than that the two songs are
+    a tie for every practical purpose and the order falls to the song id)."""
+    u1 = ds.U if u1 is None else u1
+    worst, inversions, missed = 0.0, 0, 0
+    for m in (oracle_lib.UBM, oracle_lib.IBM):
+        f = oracle_lib.fp64_scores(ds, m, u0, u1)
+        c = oracle_lib.canon_scores(ds, m, u0, u1)
+        np.testing.assert_array_equal(np.isnan(f), np.isnan(c))
+        ok = ~np.isnan(f)
+        np.testing.assert_array_equal(f[ok] == 0, c[ok] == 0)
+        nz = ok & (f != 0)
+        worst = max(worst, float(np.max(np.abs(c[nz] - f[nz]) / f[nz])) if nz.any() else 0.0)
+        cs, _, cl = oracle_lib.topk(c, k)
+        fs, fv, fl = oracle_lib.topk(f, k)
+        np.testing.assert_array_equal(cl, fl)
+        for r in range(u1 - u0):
+            n = int(cl[r])
+            fc = f[r, cs[r, :n]]                                   # fp64 scores in canonical rank order: must be non-increasing
+            drop = fc[1:] - fc[:-1]
+            inversions += int(np.count_nonzero(drop > 1e-12 * fc[:-1]))
+            if n:
+                kth = fv[r, n - 1]                                 # members: anything the canonical list lacks must tie with the k-th score
+                lacking = np.setdiff1d(fs[r, :n], cs[r, :n])
+                missed += int(np.count_nonzero(f[r, lacking] > kth * (1 + 1e-12)))
+    return worst, inversions, missed
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3"])
+def test_fp64_ranking_differential_small_configs(oracle_lib, name):
+    """Ranking the exact integers of the canonical arithmetic ranks the reference's doubles (MR:147-148, 166, 237-238, 257): on the three
+    small BASELINE shapes the top-500 lists have no inversion and no missed member beyond fp64 near-ties, and every score is within the
+    1e-5 relative tolerance north_star names (measured: ~1e-6)."""
+    ds = synth_config(name)
+    worst, inversions, missed = ranking_differential(oracle_lib, ds, 500)
+    assert worst < 1e-5
+    assert inversions == 0 and missed == 0
+
+
+def test_fp64_ranking_differential_msd_shard(oracle_lib):
+    """The same on 64 test users of the MSD-shaped configuration (BASELINE configs[3]: 909 318 train users, 384 546 songs), where the
+    degrees — and with them the fixed-point rounding — are largest: measured 1.5e-6 (UBM) / 2.0e-6 (IBM) relative, inside 1e-5."""
+    ds = synth_config("c4").shard_test_users(0, 64)
+    worst, inversions, missed = ranking_differential(oracle_lib, ds, 500)
+    assert worst < 1e-5
+    assert worst > 1e-9            # the differential is real: the two restatements do not share their arithmetic
+    assert inversions == 0 and missed == 0
+
+
+def test_fp64_restatement_equals_naive(oracle_lib):
+    """The CSR fp64 restatement is the as-written loops with ascending-id iteration order: bit-equal on small inputs."""
+    ds = synth(T=60, U=5, S=700, seed=4)
+    for m in (oracle_lib.UBM, oracle_lib.IBM):
+        n = oracle_lib.naive_scores(ds, m)
+        f = oracle_lib.fp64_scores(ds, m)
+        np.testing.assert_array_equal(np.isnan(n), np.isnan(f))
+        np.testing.assert_array_equal(np.nan_to_num(n).view(np.int64), np.nan_to_num(f).view(np.int64))
+
+
+def test_map_at_k_known_answers(oracle_lib):
+    """mAP@k (MSD-challenge definition): hand-computed cases."""
+    from musicrecommendation_b200.dataset import Dataset
+    def ds_with_labels(rows):
+        ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+        col = np.array([s for r in rows for s in sorted(r)], np.int32)
+        z = np.zeros(0, np.int32)
+        return Dataset(0, len(rows), 10, np.zeros(1, np.int64), z, np.zeros(len(rows) + 1, np.int64), z, ptr, col, z, z, z)
+    top = np.array([[3, 1, 4, 0, 5], [2, 7, 8, 9, 6], [0, 1, -1, -1, -1], [5, 6, 7, 8, 9]], np.int32)
+    ln = np.array([5, 5, 2, 5], np.int32)
+    ds = ds_with_labels([{1, 5, 9}, {2}, {1, 2, 3, 4, 5, 6, 7}, set()])
+    m, ap = oracle_lib.map_at_k(top, ln, ds, per_user=True)
+    # user 0: hits at ranks 2 and 5 -> (1/2 + 2/5) / min(3, 5); user 1: hit at rank 1 -> 1 / 1; user 2: hit at rank 2 of a 2-long list,
+    # 7 labels -> (1/2) / min(7, 5); user 3 has no labels and is skipped
+    want = [(1 / 2 + 2 / 5) / 3, 1.0, (1 / 2) / 5, 0.0]
+    np.testing.assert_array_equal(ap, want)
+    assert m == (want[0] + want[1] + want[2]) / 3
+    # a perfect ranking scores 1, one that recommends nothing relevant scores 0
+    assert oracle_lib.map_at_k(np.array([[1, 5, 9, 0, 2]], np.int32), np.array([5], np.int32), ds_with_labels([{1, 5, 9}])) == 1.0
+    assert oracle_lib.map_at_k(np.array([[0, 2, 3, 4, 6]], np.int32), np.array([5], np.int32), ds_with_labels([{1, 5, 9}])) == 0.0

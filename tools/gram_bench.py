@@ -2,7 +2,7 @@
 """Measure kernel K1 (tcgen05 int8 count GEMM) where it is the dominant cost: the item-space head-row precompute on a
 dense-friendly shape (all operands resident as dense 0/1 u8 matrices).  Prints one JSON line with dense-equivalent int8 TOP/s.
 
-  python tools_gram_bench.py [--train 131072] [--songs 32768]
+  python tools/gram_bench.py [--train 131072] [--songs 32768]
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ from pathlib import Path
 
 import numpy as np
 
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from musicrecommendation_b200 import _lib
 from musicrecommendation_b200.dataset import synth
 from musicrecommendation_b200.recommender import MusicRecommender

@@ -6,7 +6,7 @@ G_r[p0:p1, :] with kernel K1 (tcgen05 count GEMM, or the inverted-index kernel w
 summed with `reduce_scatter` (integers: exact in any order) so rank r owns rows r of every panel, and the owner applies the cosine
 normalisation g / (sqrt(d_i) sqrt(d_j)) (MusicRecommender.scala:237-238).  Verified against the oracle on the smallest shape.
 
-  torchrun --nproc-per-node N tools_gram_sweep.py --songs 10000 20000 50000
+  torchrun --nproc-per-node N tools/gram_sweep.py --songs 10000 20000 50000
 """
 import argparse
 import json
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from musicrecommendation_b200 import _lib
 from musicrecommendation_b200.dataset import synth
 from musicrecommendation_b200.distributed import split_train_users, reduce_scatter_rows

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Profiling aid (not a bench line): native GPU ingest (mr_ingest_tsv) of an MSD-shaped synthetic TSV set, stage times in ms, checked
-against the generator's own CSR.   python tools_ingest_bench.py [--config c4] [--host-sample 200000]"""
+against the generator's own CSR.   python tools/ingest_bench.py [--config c4] [--host-sample 200000]"""
 import argparse, io, json, sys, time
 from pathlib import Path
 import numpy as np
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from musicrecommendation_b200.dataset import synth_config
 from musicrecommendation_b200.recommender import dataset_from_streams, dataset_from_streams_native
 

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Profiling aid (not a bench line): per-model, per-phase CUDA-event times of one MSD-shaped step on one GPU.
-   python tools_phase_probe.py [--users N]     env MRSCORE_* tunables apply."""
+   python tools/phase_probe.py [--users N]     env MRSCORE_* tunables apply."""
 import argparse, json, sys, time
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from musicrecommendation_b200 import _lib
 from musicrecommendation_b200.dataset import synth_config
 from musicrecommendation_b200.recommender import MusicRecommender

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_sweep.sh tag "ENV=.. ENV=.." ...   (each argument = one bench configuration; profiling aid, not a bench line)
+# usage: tools/sweep.sh tag "ENV=.. ENV=.." ...   (each argument = one bench configuration; profiling aid, not a bench line)
 mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
