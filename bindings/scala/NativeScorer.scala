@@ -21,6 +21,13 @@ trait MrScore extends Library {
   def mr_evaluate_dense(h: Pointer, scoresUxS: Array[Double], nUsers: Int, nSongs: Int, labRowPtr: Array[Long], labCol: Array[Int],
                         nThresholds: Int, outMap: Array[Double]): Int
   // TSV -> int-id data model on the GPU (MusicRecommender.scala:26-91); the result object is read with mr_ingest_get(which = MR_ING_*)
+  def mr_score_users(h: Pointer, model: Int, userIdx: Array[Int], n: Int, outNxS: Array[Double]): Int   // DIST getRanks1 (distributed.scala:198-205, 269-276)
+  def mr_score_songs(h: Pointer, model: Int, songIds: Array[Int], n: Int, outNxU: Array[Double]): Int   // DIST getRanks2 (distributed.scala:214-221, 285-292)
+  def mr_map_at_k(h: Pointer, k: Int, topSong: Array[Int], topLen: Array[Int], nUsers: Int, labRowPtr: Array[Long], labCol: Array[Int],
+                  outMap: com.sun.jna.ptr.DoubleByReference, outAp: Array[Double]): Int
+  def mr_write_model(path: String, scoresUxS: Array[Double], nUsers: Int, nSongs: Int, userChars: Array[Byte], userOff: Array[Long],
+                     songChars: Array[Byte], songOff: Array[Long], append: Int, rowsWritten: LongByReference): Int   // writeModelOnFile MR:489-496
+  def mr_set_option(h: Pointer, option: Int, value: Long): Int
   def mr_ingest_tsv(device: Int, train: Array[Byte], trainLen: Long, test: Array[Byte], testLen: Long, labels: Array[Byte],
                     labelsLen: Long, out: PointerByReference): Int
   def mr_ingest_error(g: Pointer): String
