@@ -68,17 +68,19 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def make_workload(name: str, rank: int, world: int, users_total: int = 0):
+def make_workload(name: str, rank: int, world: int, users_total: int = 0, partition: str = "users"):
     from musicrecommendation_b200.dataset import synth_config
     from musicrecommendation_b200.distributed import shard_range
     t0 = time.time()
     if name == "msd":
         full = synth_config("c4")
         n_users = min(users_total or N_TEST_USERS, full.U)
-        u0, u1 = shard_range(n_users, rank, world)
+        u0, u1 = (0, n_users) if partition == "songs" else shard_range(n_users, rank, world)
         ds = full.shard_test_users(u0, u1)
-        desc = (f"BASELINE configs[3]: MSD-shaped synthetic, T={full.T} train users, S={full.S} songs, nnz_train={full.nnz_tr}, all {n_users} test users "
-                f"sharded by test user over {world} GPU(s), train replica per GPU; head-row precompute inside every step")
+        how = (f"songs partitioned over {world} GPU(s) (distributed.scala:459-461), every GPU scores all test users against its songs, all-to-all + join of the ranked lists"
+               if partition == "songs" else f"sharded by test user over {world} GPU(s)")
+        desc = (f"BASELINE configs[3]: MSD-shaped synthetic, T={full.T} train users, S={full.S} songs, nnz_train={full.nnz_tr}, all {n_users} test users, "
+                f"{how}, train replica per GPU; head-row precompute inside every step")
         total_pairs = 2 * (n_users * full.S - int(full.te_ptr[n_users]))
     else:
         full = synth_config(name)
@@ -266,6 +268,9 @@ def main():
     ap.add_argument("--no-k1-probe", action="store_true", help="skip the tensor-core count-GEMM probe")
     ap.add_argument("--users", type=int, default=0, help="profiling aid: total test users of the job instead of 110 000 (not a bench line)")
     ap.add_argument("--head-min-deg", type=int, default=-1, help="MR_OPT_HEAD_MIN_DEG (-1: picked from the batches per GPU, 0: library default)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "users", "songs"],
+                    help="msd on N > 1 GPUs: shard the test users (DIST:450-452) or partition the songs (DIST:459-461; auto = songs: the head-row "
+                         "precompute is divided by N instead of replicated)")
     ap.add_argument("--batch-users", type=int, default=0, help="MR_OPT_ITEM_BATCH: cap on test users per batch (0: as many as fit in HBM)")
     ap.add_argument("--ksplit-songs", type=int, nargs="+", default=[20000])
     ap.add_argument("--ksplit-mode", default="auto", choices=["auto", "fused", "nccl"])
@@ -304,10 +309,14 @@ def main():
 
     from musicrecommendation_b200 import _lib
     from musicrecommendation_b200.recommender import MusicRecommender
-    from musicrecommendation_b200.distributed import gather_topk_packed
+    from musicrecommendation_b200.distributed import gather_topk_packed, shard_range, song_window, exchange_song_partitions
 
     msd = args.workload == "msd"
-    ds, desc, total_pairs = make_workload(args.workload, rank, world, args.users)
+    n_job_users = min(args.users or N_TEST_USERS, N_TEST_USERS)
+    by_songs = msd and world > 1 and args.partition in ("auto", "songs") and n_job_users % world == 0    # equal user ranges: one gather of equal blocks
+    ds, desc, total_pairs = make_workload(args.workload, rank, world, args.users, "songs" if by_songs else "users")
+    window = song_window(ds.S, rank, world) if by_songs else None
+    my_u0, my_u1 = shard_range(ds.U, rank, world) if by_songs else (0, ds.U)     # the users whose joined lists this rank ends up with
     engine = {"auto": _lib.MR_ENGINE_AUTO, "tensor": _lib.MR_ENGINE_TENSOR, "sparse": _lib.MR_ENGINE_SPARSE}[args.engine]
     space = {"auto": _lib.MR_SPACE_AUTO, "user": _lib.MR_SPACE_USER, "item": _lib.MR_SPACE_ITEM}[args.space]
     # head size: a dense head row pays off when several batches of test users reuse it; a GPU that scores a single batch builds fewer
@@ -316,9 +325,9 @@ def main():
         # measured on one B200 (gpurun_out/r02_bench_u13750_md*.json): per 13 750-user batch the step costs 88.7 / 89.7 / 100.3 / 129.7 ms and the
         # precompute 130 / 113 / 57 / 35 ms at min_deg 64 / 150 / 400 / 1000 — few batches per GPU favour a small head
         batches = -(-ds.U // 13750)
-        head_min_deg = (400 if batches <= 5 else 150) if msd else 0
+        head_min_deg = 0 if by_songs else ((400 if batches <= 5 else 150) if msd else 0)
     t_load0 = time.perf_counter()
-    mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space, head_min_deg=head_min_deg, item_batch=args.batch_users)
+    mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space, head_min_deg=head_min_deg, item_batch=args.batch_users, song_window=window)
     lib, h = mr._lib, mr._h
     load_ms = 1e3 * (time.perf_counter() - t_load0)
     log(f"[rank {rank}] mr_load done in {load_ms / 1e3:.1f}s, info={mr.info()}")
@@ -333,12 +342,30 @@ def main():
     mr.prepare()                                   # cold: includes the cudaMalloc of the head rows
     cold_precompute_ms = 1e3 * (time.perf_counter() - t0)
 
+    # song partitioning: per model one joined block (song | score | len of this rank's users) that the partitions' lists are merged into
+    n_mine = my_u1 - my_u0
+    joined = {}
+    if by_songs:
+        song_b, score_b = -(-n_mine * k * 4 // 16) * 16, n_mine * k * 8
+        for model in (_lib.MR_UBM, _lib.MR_IBM):
+            block = torch.empty(song_b + score_b + -(-n_mine * 4 // 16) * 16, dtype=torch.uint8, device="cuda")
+            joined[model] = (block, block[:n_mine * k * 4].view(torch.int32).view(n_mine, k), block[song_b:song_b + score_b].view(torch.float64).view(n_mine, k),
+                             block[song_b + score_b:song_b + score_b + n_mine * 4].view(torch.int32))
+
+    def score_model(model):
+        """One model for this rank's part of the job, result left on the device."""
+        check(lib.mr_topk_device(h, model, 0.0, 0, k))
+        if by_songs:      # exchange step of the song partitioning: all-to-all of the ranked lists, then the join (mr_topk_merge), in stream order
+            with torch.cuda.stream(stream):
+                parts = exchange_song_partitions(*mr.topk_device_tensors(k), ds.U, world, rank)
+            mr.mergeTopK(*parts, *joined[model][1:])
+
     def step_device(rebuild=True):
         if rebuild and item_space:
             check(lib.mr_invalidate_prepared(h))
             check(lib.mr_prepare(h))
-        check(lib.mr_topk_device(h, _lib.MR_UBM, 0.0, 0, k))
-        check(lib.mr_topk_device(h, _lib.MR_IBM, 0.0, 0, k))
+        score_model(_lib.MR_UBM)
+        score_model(_lib.MR_IBM)
 
     def barrier():
         torch.cuda.synchronize()
@@ -370,9 +397,12 @@ def main():
 
     # ---------------- end-to-end through the host-buffer C-ABI (pinned host -> device, device -> host every step)
     keep = [pinned(ds.te_ptr.astype(np.int64)), pinned(ds.te_col.astype(np.int32)), pinned(ds.deg_te.astype(np.int32))]
-    out = [pinned(np.empty((U, k), np.int32)), pinned(np.empty((U, k), np.float64)), pinned(np.empty(U, np.int32))]
+    out = [pinned(np.empty((n_mine, k), np.int32)), pinned(np.empty((n_mine, k), np.float64)), pinned(np.empty(n_mine, np.int32))]
     h2d = sum(a.nbytes for _, a in keep)
     d2h = 2 * sum(a.nbytes for _, a in out)
+    gather_recv = {}
+    if by_songs and rank == 0:
+        gather_recv = {m: [torch.empty_like(joined[m][0]) for _ in range(world)] for m in joined}
     comm_stream = torch.cuda.Stream(device=local_rank) if world > 1 else None
 
     def p(a):
@@ -389,10 +419,19 @@ def main():
         check(lib.mr_set_test_users(h, U, p(keep[0][1]), p(keep[1][1]), p(keep[2][1]), 0, 0))
         t.append(time.perf_counter())
         for model in (_lib.MR_UBM, _lib.MR_IBM):
-            check(lib.mr_topk(h, model, 0.0, 0, k, p(out[0][1]), p(out[1][1]), p(out[2][1])))
-            if world > 1:   # the reference's `.collect` (DIST:451-478): ONE gather of the packed (song | score | len) block to rank 0,
-                            # on its own stream so that the UBM block travels while the IBM model is computed
-                gather_topk_packed(mr, k, world, rank, stream, comm_stream)
+            if by_songs:
+                score_model(model)
+                # this rank's joined lists go to the host, and — the reference's `.collect` (DIST:461) — to rank 0, both on the comm stream
+                comm_stream.wait_stream(stream)
+                with torch.cuda.stream(comm_stream):
+                    for (dst, _), src in zip(out, joined[model][1:]):
+                        dst.copy_(src, non_blocking=True)
+                    dist.gather(joined[model][0], gather_list=gather_recv.get(model), dst=0)
+            else:
+                check(lib.mr_topk(h, model, 0.0, 0, k, p(out[0][1]), p(out[1][1]), p(out[2][1])))
+                if world > 1:   # the reference's `.collect` (DIST:451-478): ONE gather of the packed (song | score | len) block to rank 0,
+                                # on its own stream so that the UBM block travels while the IBM model is computed
+                    gather_topk_packed(mr, k, world, rank, stream, comm_stream)
             t.append(time.perf_counter())
         if comm_stream is not None:
             comm_stream.synchronize()
@@ -445,7 +484,8 @@ def main():
         # dominant phase and its algorithmic bytes per launch: every operand crosses HBM once per launch
         T, nnz = ds.T, ds.nnz_tr
         sparse = info["engine"] == _lib.MR_ENGINE_SPARSE
-        Sp = (S + 31) // 32 * 32
+        Sc = int(info["n_cols"])                      # scored columns of this GPU (its song partition; S without one)
+        Sp = (Sc + 31) // 32 * 32
         # distinct head songs per batch (head = the n_head songs with most train listeners, ties by id — as mr_load selects them)
         deg_train = np.bincount(ds.tr_col, minlength=S)
         is_head = np.zeros(S, bool)
@@ -466,7 +506,7 @@ def main():
             # (8 B per (user, song) and model)
             "head_rowsum": distinct_head_rows * Sp * 6 + 2 * U * Sp * 8,
             # top-k: 1.125 (UBM) / 1.25 (IBM, + 4 B fp32 bound per song) streaming passes over the Sint rows, k results written
-            "topk": 1.125 * U * S * 8 + 1.25 * U * S * 8 + U * S * 4 + 2 * 12 * U * k,
+            "topk": 1.125 * U * Sc * 8 + 1.25 * U * Sc * 8 + U * Sc * 4 + 2 * 12 * U * k,
             # precompute: the packed head rows written once (6 B per entry) + the train CSR / CSC read
             "precompute": info["n_head"] * Sp * 6 + 8 * nnz,
         }
@@ -499,7 +539,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if msd else "weak", "vs_baseline": None, "dtype": "int64 accumulate / f64 scores", "data": "synthetic",
             "config": {"workload": desc, "k": K_TOP, "engine": ["auto", "tensor", "sparse"][info["engine"]],
                        "space": {8: "user", 16: "item"}.get(info["space"]), "head_songs": info["n_head"], "users_per_gpu": U, "users_per_batch": batch,
-                       "batches_per_gpu": n_batches,
+                       "batches_per_gpu": n_batches, "partition": "songs" if by_songs else "test users", "songs_per_gpu": Sc,
                        "l2": "inputs (head rows >= 10 GB rebuilt every step, train CSR/CSC 0.7 GB, the Sint panel of a batch: 8 B per (user, song)) exceed the 126 MB L2; no explicit flush",
                        "pairs_per_step": total_pairs},
             "e2e": {"value": total_pairs * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -512,25 +552,32 @@ def main():
         }
         # mAP@500 of this rank's users from the device-resident lists (north_star's second parity target)
         map500 = {}
+        mine = ds.shard_test_users(my_u0, my_u1) if by_songs else ds
+        final = {}
         for name, model in (("ubm", _lib.MR_UBM), ("ibm", _lib.MR_IBM)):
-            check(lib.mr_topk_device(h, model, 0.0, 0, k))
-            map500[name] = mr.mapAtK(k)
-        line["map_at_500"] = dict(map500, users=U, what="MSD-challenge mAP@500 of rank 0's test users against their hidden halves (mr_map_at_k)")
+            if by_songs:        # rank 0's users: the joined lists of the last step
+                torch.cuda.synchronize()
+                final[name] = tuple(t.cpu().numpy() for t in joined[model][1:])
+                map500[name] = mr.mapAtK(k, top=(final[name][0], final[name][2]), labels=mine)
+            else:
+                check(lib.mr_topk_device(h, model, 0.0, 0, k))
+                map500[name] = mr.mapAtK(k)
+        line["map_at_500"] = dict(map500, users=mine.U, what="MSD-challenge mAP@500 of rank 0's test users against their hidden halves (mr_map_at_k)")
         if not args.no_cpu_baseline:
             import oracle
-            pairs_c, sec_c, thr, tops = cpu_port_sample(ds, args.ref_users)
+            pairs_c, sec_c, thr, tops = cpu_port_sample(mine, args.ref_users)
             # full-size parity: the same users' top-500 from the CUDA path must equal the oracle's bit for bit, and so must mAP@500
-            n_chk = min(args.ref_users, U)
-            sub = ds.shard_test_users(0, n_chk)
+            n_chk = min(args.ref_users, mine.U)
+            sub = mine.shard_test_users(0, n_chk)
             equal = {}
             map_equal = {}
             for name, model, (ws, wv, wl) in (("ubm", _lib.MR_UBM, tops[0]), ("ibm", _lib.MR_IBM, tops[1])):
-                gs, gv, gl = mr.getTopK(model, k=k)
+                gs, gv, gl = final[name] if by_songs else mr.getTopK(model, k=k)
                 equal[name] = bool(np.array_equal(gs[:n_chk], ws) and np.array_equal(gv[:n_chk].view(np.int64), wv.view(np.int64))
                                    and np.array_equal(gl[:n_chk], wl))
-                map_equal[name] = bool(oracle.map_at_k(gs, gl, ds) == map500[name] and oracle.map_at_k(gs[:n_chk], gl[:n_chk], sub) == oracle.map_at_k(ws, wl, sub))
+                map_equal[name] = bool(oracle.map_at_k(gs, gl, mine) == map500[name] and oracle.map_at_k(gs[:n_chk], gl[:n_chk], sub) == oracle.map_at_k(ws, wl, sub))
             line["parity"] = {"users_checked": n_chk, "top500_ids_and_scores_bit_equal": equal, "map_at_500_identical": map_equal}
-            line["cpu_baseline_as_written"] = as_written_sample(ds) if not args.no_as_written else None
+            line["cpu_baseline_as_written"] = as_written_sample(mine) if not args.no_as_written else None
             if args.workload in ("c1", "c2") and not args.no_as_written:
                 line["cpu_baseline_naive_seq_par"] = naive_legs(ds, args.workload)
             line["cpu_baseline"] = {"value": pairs_c / sec_c, "unit": "pairs/s", "cores": thr, "kind": "port",

@@ -89,7 +89,13 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
  * listeners (0 = default max(2, S / 6000), the optimum when the rows are reused by many shards; a one-shot job over few test users is
  * faster with a smaller head, bench.py picks it from the number of shards per GPU).  MR_OPT_ITEM_BATCH: upper bound on the test users
  * per item-space batch (0 = as many as fit in HBM).  Results never depend on either. */
-enum { MR_OPT_HEAD_MIN_DEG = 1, MR_OPT_ITEM_BATCH = 2 };
+enum { MR_OPT_HEAD_MIN_DEG = 1, MR_OPT_ITEM_BATCH = 2, MR_OPT_SONG_WINDOW_LO = 3, MR_OPT_SONG_WINDOW_HI = 4 };
+/* Song window (both before mr_load): the handle scores only the songs [LO, HI) of every test user — the reference's second
+ * partitioning, `ctx.parallelize(songs, 4).map(getRanks2)` (DIST:214-221, 285-292, 459-461, 477-479): one partition of songs against ALL
+ * test users.  Everything that is indexed by a scored column shrinks to HI - LO entries (head rows, score panels, mr_score_dense /
+ * mr_score_users rows, the valid ids of mr_score_songs); the train set, the test histories and every degree are still the whole data
+ * set's, so each score has the same bits as without a window.  mr_topk then ranks inside the window (ids are global song ids); the lists
+ * of the partitions of one test user are joined by mr_topk_merge.  Needs MR_ENGINE_SPARSE and MR_SPACE_ITEM (AUTO selects them). */
 int mr_set_option(mr_handle* h, int option, int64_t value);
 
 /* Build the item-space head rows (G, Gq of the popular songs) now instead of lazily on the first scoring call
@@ -178,6 +184,13 @@ int mr_topk_device_ptrs(mr_handle* h, int k, void** song, void** score, void** l
 /* The three arrays live in ONE device block (song | score | len at the returned byte offsets), so the whole result of a shard travels
  * in a single transfer — one NCCL gather to the rank that plays the Spark driver instead of three collectives. */
 int mr_topk_packed(mr_handle* h, int k, void** base, uint64_t* bytes, uint64_t* score_offset, uint64_t* len_offset);
+/* Join the ranked lists that n_parts song partitions produced for the same n_users test users (the driver-side `.collect` of DIST:461, 479
+ * followed by the ranking): part_song[p] / part_score[p] / part_len[p] are DEVICE arrays ([n_users, k] int32, [n_users, k] double,
+ * [n_users] int32, each list ordered by (score descending, song id ascending) as mr_topk leaves it); out_* are device arrays of the same
+ * shapes and receive the first min(k, sum of lengths) entries of the merged order.  Exact: the global top-k is contained in the union of
+ * the partitions' top-k.  Runs on the handle's stream (mr_stream); the pointer tables themselves are host memory. */
+int mr_topk_merge(mr_handle* h, int k, int n_parts, int n_users, const int32_t* const* part_song, const double* const* part_score,
+                  const int32_t* const* part_len, int32_t* out_song, double* out_score, int32_t* out_len);
 
 /* ---- ingest: `new MusicRecommender(trainFile, testFile, testLabelsFile)` (MR:12, 26-91) on the GPU ----------------------------------
  * The three TSV files as byte buffers (`user \t song \t count` per line, third field ignored, MR:35) become the int-id data model
@@ -217,7 +230,8 @@ int mr_reset_timing(mr_handle* h);
 int mr_set_profile(mr_handle* h, int on);                   /* toggle MR_PROFILE at run time (it synchronises after every phase) */
 int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated, space, n_head songs,
                                                                  test entries on head songs, test entries on tail songs, head-row exceptions,
-                                                                 test users per batch, head_rowsum work groups per batch, users split over groups] */
+                                                                 test users per batch, head_rowsum work groups per batch, users split over groups,
+                                                                 scored columns (= songs of the window), first song of the window] */
 void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
 
 #ifdef __cplusplus

@@ -12,7 +12,7 @@ MR_UBM, MR_IBM, MR_LC, MR_AGG, MR_STOCH = range(5)
 MR_ENGINE_AUTO, MR_ENGINE_TENSOR, MR_ENGINE_SPARSE = 0, 1, 2
 MR_PROFILE = 4
 MR_SPACE_AUTO, MR_SPACE_USER, MR_SPACE_ITEM = 0, 8, 16
-MR_OPT_HEAD_MIN_DEG, MR_OPT_ITEM_BATCH = 1, 2
+MR_OPT_HEAD_MIN_DEG, MR_OPT_ITEM_BATCH, MR_OPT_SONG_WINDOW_LO, MR_OPT_SONG_WINDOW_HI = 1, 2, 3, 4
 (MR_ING_TR_PTR, MR_ING_TR_COL, MR_ING_TE_PTR, MR_ING_TE_COL, MR_ING_LAB_PTR, MR_ING_LAB_COL, MR_ING_DEG_TRAIN, MR_ING_DEG_TEST, MR_ING_DEG_SONG,
  MR_ING_TRAIN_USER_CHARS, MR_ING_TRAIN_USER_OFF, MR_ING_TEST_USER_CHARS, MR_ING_TEST_USER_OFF, MR_ING_SONG_CHARS, MR_ING_SONG_OFF, MR_ING_TIMING_MS) = range(16)
 TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
@@ -20,7 +20,7 @@ TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "preco
 # every symbol include/mrscore.h declares
 SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device", "mr_gram_rows_scatter", "mr_peer_alloc", "mr_peer_open", "mr_peer_close",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_evaluate_dense", "mr_topk", "mr_topk_device",
-           "mr_topk_fetch", "mr_topk_device_ptrs", "mr_set_option", "mr_invalidate_prepared", "mr_score_users", "mr_score_songs", "mr_map_at_k", "mr_write_model", "mr_format_double", "mr_topk_packed", "mr_gram_rows_scatter_async", "mr_peer_signal", "mr_peer_wait", "mr_sync", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream",
+           "mr_topk_fetch", "mr_topk_device_ptrs", "mr_set_option", "mr_invalidate_prepared", "mr_score_users", "mr_score_songs", "mr_map_at_k", "mr_write_model", "mr_format_double", "mr_topk_packed", "mr_topk_merge", "mr_gram_rows_scatter_async", "mr_peer_signal", "mr_peer_wait", "mr_sync", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream",
            "mr_ingest_tsv", "mr_ingest_error", "mr_ingest_dims", "mr_ingest_get", "mr_ingest_free"]
 
 _lib = None
@@ -75,6 +75,7 @@ def load():
     lib.mr_write_model.argtypes = [C.c_char_p, vp, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i64)]
     lib.mr_format_double.argtypes = [dbl, C.c_char_p]
     lib.mr_topk_packed.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    lib.mr_topk_merge.argtypes = [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp]
     lib.mr_gram_rows_scatter_async.argtypes = [vp, i32, i32, C.POINTER(vp), i32, i32, i64]
     lib.mr_peer_signal.argtypes = [vp, C.POINTER(vp), i32, u64]
     lib.mr_peer_wait.argtypes = [vp, vp, i32, u64]

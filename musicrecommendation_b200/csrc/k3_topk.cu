@@ -25,11 +25,12 @@ __device__ __forceinline__ double blend_score(int model, long long su, long long
 }
 
 // ---------------------------------------------------------------- listened-pair sentinel (getModel's filter, MR:109)
-__global__ void mask_listened_kernel(const long long* __restrict__ te_ptr, const int* __restrict__ te_col, int u0, int n_users,
-                                     long long* sint_u, long long* sint_i, long long spitch) {
+// te_end[u] = end of the row's scored columns: te_ptr[u + 1], or — with a song window — the end of the in-window prefix of the row
+__global__ void mask_listened_kernel(const long long* __restrict__ te_ptr, const long long* __restrict__ te_end, const int* __restrict__ te_col,
+                                     int u0, int n_users, long long* sint_u, long long* sint_i, long long spitch) {
   const int b = blockIdx.x;
   if (b >= n_users) return;
-  const long long beg = te_ptr[u0 + b], end = te_ptr[u0 + b + 1];
+  const long long beg = te_ptr[u0 + b], end = te_end[u0 + b];
   for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const int s = te_col[i];
     if (sint_u) sint_u[static_cast<long long>(b) * spitch + s] = kListened;
@@ -37,10 +38,10 @@ __global__ void mask_listened_kernel(const long long* __restrict__ te_ptr, const
   }
 }
 
-int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
-                         long long spitch, cudaStream_t st) {
+int launch_mask_listened(const long long* te_ptr, const long long* te_end, const int* te_col, int u0, int n_users, long long* sint_u,
+                         long long* sint_i, long long spitch, cudaStream_t st) {
   if (n_users <= 0) return 0;
-  mask_listened_kernel<<<n_users, 128, 0, st>>>(te_ptr, te_col, u0, n_users, sint_u, sint_i, spitch);
+  mask_listened_kernel<<<n_users, 128, 0, st>>>(te_ptr, te_end, te_col, u0, n_users, sint_u, sint_i, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -107,7 +108,7 @@ __global__ void select_bits_kernel(BlendParams bp, const long long* __restrict__
   const int b = blockIdx.y;
   const int u = u0 + b;
   const int n_words = (n_songs + 63) / 64;
-  const long long beg = te_ptr[u], end = te_ptr[u + 1];
+  const long long beg = te_ptr[u], end = bp.te_end[u];
   const int* row = te_col + beg;
   const int row_len = static_cast<int>(end - beg);
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
@@ -150,8 +151,8 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 // One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
 // the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
 // Every bin map below is monotone in the key and only ever a PRE-FILTER; exactness comes from the final sort of the collected keys.
-//   long rows (S > 65536), fast path — 1.25 passes over the row:
-//     A1  maximum over every 8th chunk of the row (1/8 of it)
+//   long rows (S > 16384), fast path — 1.25 passes over the row (1.5 below 65 536 songs):
+//     A1  maximum over every 8th chunk of the row (1/8 of it; every 4th chunk for rows of up to 65 536 songs)
 //     A2  2048-bin logarithmic histogram (64 bins per binade below the maximum) over the same chunks; the bin above which about
 //         (k + k/2) / 8 sampled keys lie gives the cut
 //     B   ONE full pass collects the keys at or above the cut; accepted when min(k, valid) <= collected <= 2048
@@ -477,8 +478,8 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
 
-  const int stride = n_songs > 65536 ? 8 : 1;
-  const int n_valid = n_songs - static_cast<int>(te_ptr[u + 1] - te_ptr[u]);   // scored pairs of this user (MR:109)
+  const int stride = n_songs > 65536 ? 8 : (n_songs > 16384 ? 4 : 1);   // rows of a song partition (S / 8 = 48 k songs at MSD scale) sample every 4th chunk
+  const int n_valid = n_songs - static_cast<int>(bp.te_end[u] - te_ptr[u]);   // scored pairs of this user (MR:109)
   int need = 0;
   bool collected = false;
   double max_score = 0.0;
@@ -627,7 +628,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
     }
   }
   for (int i = tid; i < k; i += kTopkThreads) {
-    if (i < need) { o_song[i] = s_song[i]; o_score[i] = __longlong_as_double(static_cast<long long>(s_key[i])); }
+    if (i < need) { o_song[i] = s_song[i] + bp.song_off; o_score[i] = __longlong_as_double(static_cast<long long>(s_key[i])); }
     else { o_song[i] = -1; o_score[i] = 0.0; }
   }
   if (tid == 0) out_len[u] = need;
@@ -640,6 +641,63 @@ int launch_topk(const BlendParams& bp, const long long* te_ptr, const long long*
   if (k <= 0 || k > kTopkCap / 2) return -2;
   topk_kernel<<<n_users, kTopkThreads, 0, st>>>(bp, te_ptr, sint_u, sint_i, spitch, sel, sel_pitch_words, u0, n_songs, rsa, rsd, k,
                                                 out_song, out_score, out_len);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- join of the ranked lists of several song partitions
+// One CTA per test user.  The n lists (each ordered by score descending, song id ascending — disjoint song sets, so the order over their
+// union is strict) are staged in shared memory; an element's position in the merged order is its own index plus, for every other list,
+// the number of that list's elements that precede it (one binary search each); the first k positions are written.  This is the
+// driver-side `.collect` + ranking of the reference's song partitioning (distributed.scala:459-461, 477-479).
+__device__ __forceinline__ bool merge_precedes(double sa, int ia, double sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
+
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(MergeParts p, int k, int n_users, int* __restrict__ out_song, double* __restrict__ out_score, int* __restrict__ out_len) {
+  extern __shared__ double s_merge[];
+  double* s_score = s_merge;                                             // [n][k]
+  int* s_song = reinterpret_cast<int*>(s_merge + p.n * k);              // [n][k]
+  __shared__ int s_len[kMergeMaxParts];
+  const int u = blockIdx.x;
+  if (u >= n_users) return;
+  if (threadIdx.x < p.n) s_len[threadIdx.x] = max(0, min(k, p.len[threadIdx.x][u]));
+  __syncthreads();
+  for (int a = 0; a < p.n; ++a) {
+    const int la = s_len[a];
+    for (int i = threadIdx.x; i < la; i += blockDim.x) {
+      s_score[a * k + i] = p.score[a][static_cast<long long>(u) * k + i];
+      s_song[a * k + i] = p.song[a][static_cast<long long>(u) * k + i];
+    }
+  }
+  int total = 0;
+  for (int a = 0; a < p.n; ++a) total += s_len[a];
+  const int need = min(k, total);
+  __syncthreads();
+  int* o_song = out_song + static_cast<long long>(u) * k;
+  double* o_score = out_score + static_cast<long long>(u) * k;
+  for (int e = threadIdx.x; e < p.n * k; e += blockDim.x) {
+    const int a = e / k, i = e - a * k;
+    if (i >= s_len[a]) continue;
+    const double sc = s_score[e]; const int sg = s_song[e];
+    int rank = i;
+    for (int b = 0; b < p.n && rank < need; ++b) {
+      if (b == a) continue;
+      int lo = 0, hi = s_len[b];                                        // elements of list b that precede (sc, sg)
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (merge_precedes(s_score[b * k + m], s_song[b * k + m], sc, sg)) lo = m + 1; else hi = m; }
+      rank += lo;
+    }
+    if (rank < need) { o_song[rank] = sg; o_score[rank] = sc; }
+  }
+  for (int i = need + threadIdx.x; i < k; i += blockDim.x) { o_song[i] = -1; o_score[i] = 0.0; }
+  if (threadIdx.x == 0) out_len[u] = need;
+}
+
+int launch_merge_topk(const MergeParts& p, int k, int n_users, int* out_song, double* out_score, int* out_len, cudaStream_t st) {
+  if (n_users <= 0) return 0;
+  if (p.n < 1 || p.n > kMergeMaxParts || k < 1) return -2;
+  const size_t smem = static_cast<size_t>(p.n) * k * 12;
+  if (smem > 200 * 1024) return -3;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -4;
+  merge_topk_kernel<<<n_users, 256, smem, st>>>(p, k, n_users, out_song, out_score, out_len);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -33,8 +33,8 @@ template <bool kPacked>
 __global__ void __launch_bounds__(256)
 gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int r0, int r1,
                          const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
-                         const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
-                         uint32_t* __restrict__ g, unsigned long long* __restrict__ gq, long long pitch) {
+                         const long long* __restrict__ tr_ptr, const long long* __restrict__ tr_end, const int* __restrict__ tr_col,
+                         const uint32_t* __restrict__ qv, uint32_t* __restrict__ g, unsigned long long* __restrict__ gq, long long pitch) {
   const int lane = threadIdx.x & 31;
   const long long w0 = lst_ptr[r0], w1 = lst_ptr[r1];
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -45,7 +45,7 @@ gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __r
     const int j = head_song[h];
     const int v = csc_idx[csc_ptr[j] + (w - lst_ptr[h])];
     const unsigned long long q = kPacked ? (static_cast<unsigned long long>(qv[v]) + (1ULL << kPackShift)) : qv[v];
-    const long long b = tr_ptr[v], e = tr_ptr[v + 1];
+    const long long b = tr_ptr[v], e = tr_end[v];
     for (long long m = b + lane; m < e; m += 32) {
       const int s = __ldg(tr_col + m);
       if (!kPacked) atomicAdd(g + static_cast<long long>(h - r0) * pitch + s, 1u);
@@ -55,16 +55,16 @@ gram_head_scatter_kernel(const int* __restrict__ head_song, const long long* __r
 }
 
 int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
-                             const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
-                             long long pitch, int packed, int num_sms, cudaStream_t st) {
+                             const long long* tr_ptr, const long long* tr_end, const int* tr_col, const uint32_t* qv, uint32_t* g,
+                             unsigned long long* gq, long long pitch, int packed, int num_sms, cudaStream_t st) {
   if (r1 <= r0) return 0;
   cudaError_t e = cudaSuccess;
   if (!packed) e = cudaMemsetAsync(g, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint32_t), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(gq, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return -1;
   // exits at once where a chunk has little work
-  if (packed) gram_head_scatter_kernel<true><<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
-  else gram_head_scatter_kernel<false><<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g, gq, pitch);
+  if (packed) gram_head_scatter_kernel<true><<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, g, gq, pitch);
+  else gram_head_scatter_kernel<false><<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, g, gq, pitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -78,8 +78,8 @@ int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int
 __global__ void __launch_bounds__(256)
 gram_head_direct_kernel(const int* __restrict__ head_song, const long long* __restrict__ lst_ptr, int r0, int r1,
                         const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
-                        const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
-                        uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, long long pitch) {
+                        const long long* __restrict__ tr_ptr, const long long* __restrict__ tr_end, const int* __restrict__ tr_col,
+                        const uint32_t* __restrict__ qv, uint16_t* __restrict__ g16, uint32_t* __restrict__ gq32, long long pitch) {
   const int lane = threadIdx.x & 31;
   const long long w0 = lst_ptr[r0], w1 = lst_ptr[r1];
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -92,7 +92,7 @@ gram_head_direct_kernel(const int* __restrict__ head_song, const long long* __re
     const int v = csc_idx[csc_ptr[j] + (w - lst_ptr[h])];
     const uint32_t q = qv[v];
     const long long row = static_cast<long long>(h) * pitch;   // pitch is a multiple of 32: the parity of row + s is the parity of s
-    const long long b = tr_ptr[v], e = tr_ptr[v + 1];
+    const long long b = tr_ptr[v], e = tr_end[v];
     for (long long m = b + lane; m < e; m += 32) {
       const int s = __ldg(tr_col + m);
       atomicAdd(gq32 + row + s, q);
@@ -102,13 +102,13 @@ gram_head_direct_kernel(const int* __restrict__ head_song, const long long* __re
 }
 
 int launch_gram_head_direct(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
-                            const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint16_t* g16, uint32_t* gq32,
-                            long long pitch, int num_sms, cudaStream_t st) {
+                            const long long* tr_ptr, const long long* tr_end, const int* tr_col, const uint32_t* qv, uint16_t* g16,
+                            uint32_t* gq32, long long pitch, int num_sms, cudaStream_t st) {
   if (r1 <= r0) return 0;
   cudaError_t e = cudaMemsetAsync(g16 + static_cast<long long>(r0) * pitch, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint16_t), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(gq32 + static_cast<long long>(r0) * pitch, 0, static_cast<size_t>(r1 - r0) * pitch * sizeof(uint32_t), st);
   if (e != cudaSuccess) return -1;
-  gram_head_direct_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, g16, gq32, pitch);
+  gram_head_direct_kernel<<<num_sms * 8, 256, 0, st>>>(head_song, lst_ptr, r0, r1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, g16, gq32, pitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -310,9 +310,9 @@ template <int kModels>
 __global__ void __launch_bounds__(256)
 tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_song, const long long* __restrict__ tu_lptr,
                     long long e0, long long e1, const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
-                    const long long* __restrict__ tr_ptr, const int* __restrict__ tr_col, const uint32_t* __restrict__ qv,
-                    const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u, long long* __restrict__ sint_i,
-                    long long spitch) {
+                    const long long* __restrict__ tr_ptr, const long long* __restrict__ tr_end, const int* __restrict__ tr_col,
+                    const uint32_t* __restrict__ qv, const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u,
+                    long long* __restrict__ sint_i, long long spitch) {
   const int lane = threadIdx.x & 31;
   const long long w0 = tu_lptr[e0], w1 = tu_lptr[e1];
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -326,7 +326,7 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
     const unsigned long long q = qv[v], qj = qd[j];
     unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
-    const long long rb = tr_ptr[v], re = tr_ptr[v + 1];
+    const long long rb = tr_ptr[v], re = tr_end[v];
     for (long long m = rb + lane; m < re; m += 32) {
       const int s = __ldg(tr_col + m);
       if (s == j) continue;
@@ -337,15 +337,16 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
 }
 
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
-                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
-                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs, cudaStream_t st) {
+                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const long long* tr_end, const int* tr_col,
+                        const uint32_t* qv, const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs,
+                        cudaStream_t st) {
   if (e1 <= e0 || n_pairs <= 0) return 0;
   // one warp per (entry, listener) pair in short-lived CTAs (measured 25 % faster than a persistent grid-stride grid: the block
   // scheduler balances the 1..4000-song listeners better than a static stride does)
   const int grid = static_cast<int>(std::min<long long>((n_pairs + 7) / 8, 1LL << 30));
-  if (models == 1) tail_scatter_kernel<1><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else if (models == 2) tail_scatter_kernel<2><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else tail_scatter_kernel<3><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  if (models == 1) tail_scatter_kernel<1><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else if (models == 2) tail_scatter_kernel<2><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  else tail_scatter_kernel<3><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

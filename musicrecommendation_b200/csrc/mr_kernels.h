@@ -69,11 +69,11 @@ struct HeadExceptions {      // entries of the packed head rows whose count exce
   int* row; int* song; uint32_t* g_extra; unsigned long long* gq_extra;
 };
 int launch_gram_head_scatter(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
-                             const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint32_t* g, unsigned long long* gq,
-                             long long pitch, int packed, int num_sms, cudaStream_t st);
+                             const long long* tr_ptr, const long long* tr_end, const int* tr_col, const uint32_t* qv, uint32_t* g,
+                             unsigned long long* gq, long long pitch, int packed, int num_sms, cudaStream_t st);
 int launch_gram_head_direct(const int* head_song, const long long* lst_ptr, int r0, int r1, const long long* csc_ptr, const int* csc_idx,
-                            const long long* tr_ptr, const int* tr_col, const uint32_t* qv, uint16_t* g16, uint32_t* gq32,
-                            long long pitch, int num_sms, cudaStream_t st);
+                            const long long* tr_ptr, const long long* tr_end, const int* tr_col, const uint32_t* qv, uint16_t* g16,
+                            uint32_t* gq32, long long pitch, int num_sms, cudaStream_t st);
 int launch_pack_head_rows(const uint32_t* g, const unsigned long long* gq, int packed, int r0, int n_rows, long long pitch, int n_songs,
                           uint16_t* g16, uint32_t* gq32, HeadExceptions ex, int num_sms, cudaStream_t st);
 // model: 1 = UBM pass over Gq32, 2 = IBM pass over G16; words = 32-bit words per row load (1, 2 or 4); threads per CTA (a CTA covers
@@ -86,8 +86,9 @@ int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, co
                       const long long* ex_ptr, const int* ex_song, const uint32_t* ex_g, const unsigned long long* ex_gq,
                       long long* sint_u, long long* sint_i, long long spitch, cudaStream_t st);
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
-                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const int* tr_col, const uint32_t* qv,
-                        const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs, cudaStream_t st);
+                        const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const long long* tr_end, const int* tr_col,
+                        const uint32_t* qv, const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs,
+                        cudaStream_t st);
 
 // ---- per-shard work lists of the item-space engine, built on the device (k7_testlists.cu)
 size_t test_lists_temp_bytes(long long nnz);
@@ -99,8 +100,8 @@ int launch_gather_group_entries(const int4* desc, int n_desc, const int* hu_row,
                                 cudaStream_t st);
 
 // ---- K3 (k3_topk.cu)
-int launch_mask_listened(const long long* te_ptr, const int* te_col, int u0, int n_users, long long* sint_u, long long* sint_i,
-                         long long spitch, cudaStream_t st);
+int launch_mask_listened(const long long* te_ptr, const long long* te_end, const int* te_col, int u0, int n_users, long long* sint_u,
+                         long long* sint_i, long long spitch, cudaStream_t st);
 int launch_dense_scores(int model, const long long* sint, long long spitch, int u0, int n_users, int n_songs, const double* rsa,
                         const double* rsd, double* out, cudaStream_t st);
 struct BlendParams {
@@ -112,12 +113,17 @@ struct BlendParams {
   const long long* pair_base;  // [U+1] exclusive prefix of per-user scored-pair counts (index in MAIN:57-59 order)
   const float* rsd_up;       // [S] rsd rounded up to fp32 (upper bounds for the IBM pre-filter of the top-k select), or null
   int ubm_int_ok;            // every UBM numerator of the shard is < 2^52: (double)Sint * rsu is strictly monotone in Sint, top-k may compare integers
+  const long long* te_end;   // [U] end of each test row's scored columns: te_ptr + 1, or the in-window prefix ends (song window)
+  int song_off;              // added to the ranked column ids: first song of the window (0 without one)
 };
 int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,
                        uint64_t* sel, long long sel_pitch_words, cudaStream_t st);
 int launch_topk(const BlendParams& bp, const long long* te_ptr, const long long* sint_u, const long long* sint_i, long long spitch, const uint64_t* sel,
                 long long sel_pitch_words, int u0, int n_users, int n_songs, const double* rsa, const double* rsd, int k,
                 int* out_song, double* out_score, int* out_len, cudaStream_t st);
+constexpr int kMergeMaxParts = 16;   // song partitions whose ranked lists one launch_merge_topk joins
+struct MergeParts { const int* song[kMergeMaxParts]; const double* score[kMergeMaxParts]; const int* len[kMergeMaxParts]; int n; };
+int launch_merge_topk(const MergeParts& p, int k, int n_users, int* out_song, double* out_score, int* out_len, cudaStream_t st);
 int launch_gather_columns(const double* dense, int n_rows, int n_songs, const int* songs, int n_sel, double* out, long long out_ld, int u_base,
                           cudaStream_t st);
 int launch_blend_arrays(const BlendParams& bp, const double* ubm, const double* ibm, double* out, long long n, long long first_index,

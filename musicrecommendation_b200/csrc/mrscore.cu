@@ -45,6 +45,12 @@ struct mr_handle {
   // train
   int T = 0, S = 0; long long nnz_tr = 0; bool loaded = false;
   long long *d_tr_ptr = nullptr, *d_csc_ptr = nullptr; int *d_tr_col = nullptr, *d_csc_idx = nullptr;
+  // Song window (MR_OPT_SONG_WINDOW_LO / _HI, the song partition of distributed.scala:459-461): only the songs [win_lo, win_hi) are scored.
+  // Internally song ids are ROTATED by win_lo (id' = id - win_lo mod S), so that the scored columns are [0, n_cols) of every array and
+  // kernel while histories still refer to all S songs; CSR rows stay ascending (their in-window entries become a prefix that ends at
+  // d_tr_end[v] / d_te_end[u]); only the ranked ids handed back are shifted by win_lo again.  Without a window n_cols = S, *_end = *_ptr + 1.
+  int win_lo = 0, win_hi = 0, n_cols = 0; bool windowed = false;
+  const long long *d_tr_end = nullptr, *d_te_end = nullptr;
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
   struct SongInfo { int head; uint32_t v; };   // head row or -1; v = q_26(d_s) of a head song, train listeners of a tail song
@@ -76,7 +82,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_EX_PTR, SL_EX_SONG, SL_EX_G, SL_EX_GQ, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_PACK, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_EX_PTR, SL_EX_SONG, SL_EX_G, SL_EX_GQ, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_PACK, SL_TE_END, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -382,13 +388,13 @@ int ensure_head_rows(mr_handle* h) {
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_count_gemm failed: rc=%d (%s)", lrc, cudaGetErrorString(cudaGetLastError())));
     } else {
       PhaseTimer t(h, MR_T_PRECOMPUTE);
-      int lrc = launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                         h->d_qv, g_stage, gq_stage, h->spitch, packed ? 1 : 0, h->num_sms, h->stream);
+      int lrc = launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_end,
+                                         h->d_tr_col, h->d_qv, g_stage, gq_stage, h->spitch, packed ? 1 : 0, h->num_sms, h->stream);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_scatter failed"));
     }
     PhaseTimer t(h, MR_T_PRECOMPUTE);
-    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->S, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
+    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->n_cols, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
     h->launches++;
     if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_pack_head_rows failed"));
   }
@@ -401,8 +407,8 @@ int ensure_head_rows(mr_handle* h) {
     PhaseTimer t(h, MR_T_PRECOMPUTE);
     for (int r0 = n_staged; r0 < h->n_head; r0 += static_cast<int>(dchunk)) {
       const int nr = std::min<int>(static_cast<int>(dchunk), h->n_head - r0);
-      int lrc = launch_gram_head_direct(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_col,
-                                        h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, h->stream);
+      int lrc = launch_gram_head_direct(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_end,
+                                        h->d_tr_col, h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, h->stream);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_direct failed"));
     }
@@ -574,12 +580,12 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
         if (need_ubm) {
           if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_u, h->spitch, h->stream));
           MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
-                                          h->spitch, h->S, h->d_sint_u, h->spitch, h->stream));
+                                          h->spitch, h->n_cols, h->d_sint_u, h->spitch, h->stream));
         }
         if (need_ibm) {
           if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_i, h->spitch, h->stream));
           MR_LAUNCH(h, launch_head_rowsum(2, h->head_words_i, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
-                                          h->spitch, h->S, h->d_sint_i, h->spitch, h->stream));
+                                          h->spitch, h->n_cols, h->d_sint_i, h->spitch, h->stream));
         }
         if (h->n_ex > 0)
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
@@ -597,7 +603,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           PhaseTimer t(h, MR_T_TAIL_SCATTER);
           const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
           MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                           h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
+                                           h->d_tr_end, h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
         }
         if (mode != RUN_TOPK) continue;
         PhaseTimer t(h, MR_T_TOPK);
@@ -605,9 +611,9 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
         long long* si = need_ibm ? h->d_sint_i + static_cast<long long>(s0) * h->spitch : nullptr;
         uint64_t* sel = sel_needed ? h->d_sel + static_cast<long long>(s0) * h->sel_pitch : nullptr;
         const int u0 = b0 + s0;
-        MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_col, u0, sn, su, si, h->spitch, h->stream));
-        if (sel_needed) MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, u0, sn, h->S, sel, h->sel_pitch, h->stream));
-        MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, su, si, h->spitch, sel, h->sel_pitch, u0, sn, h->S, h->d_rsa, h->d_rsd, k, h->d_out_song,
+        MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_end, h->d_te_col, u0, sn, su, si, h->spitch, h->stream));
+        if (sel_needed) MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, u0, sn, h->n_cols, sel, h->sel_pitch, h->stream));
+        MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, su, si, h->spitch, sel, h->sel_pitch, u0, sn, h->n_cols, h->d_rsa, h->d_rsd, k, h->d_out_song,
                                  h->d_out_score, h->d_out_len, h->stream));
         if (ho) {
           MR_CUDA(h, cudaEventRecord(h->ev_slice, h->stream));
@@ -671,34 +677,34 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
                                         h->spitch, h->stream));
     }
     PhaseTimer t(h, MR_T_TOPK);
-    MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_col, b0, nb, need_ubm ? h->d_sint_u : nullptr,
+    MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_end, h->d_te_col, b0, nb, need_ubm ? h->d_sint_u : nullptr,
                                       need_ibm ? h->d_sint_i : nullptr, h->spitch, h->stream));
     if (mode == RUN_DENSE) {
       for (int c0 = 0; c0 < nb; c0 += kDenseChunk) {
         const int cn = std::min(kDenseChunk, nb - c0);
         MR_LAUNCH(h, launch_dense_scores(model, (need_ubm ? h->d_sint_u : h->d_sint_i) + static_cast<long long>(c0) * h->spitch, h->spitch, b0 + c0, cn,
-                                         h->S, h->d_rsa, h->d_rsd, h->d_dense, h->stream));
+                                         h->n_cols, h->d_rsa, h->d_rsd, h->d_dense, h->stream));
         const DenseOut* dout = static_cast<const DenseOut*>(host_out);
         if (dout->kind == DenseOut::ALL) {
-          MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(b0 + c0) * h->S, h->d_dense,
-                                     static_cast<size_t>(cn) * h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+          MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(b0 + c0) * h->n_cols, h->d_dense,
+                                     static_cast<size_t>(cn) * h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         } else if (dout->kind == DenseOut::USERS) {
           for (int i = 0; i < dout->n_ids; ++i) {
             const int r = dout->ids[i] - (b0 + c0);
             if (r < 0 || r >= cn) continue;
-            MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(i) * h->S, h->d_dense + static_cast<long long>(r) * h->S,
-                                       static_cast<size_t>(h->S) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            MR_CUDA(h, cudaMemcpyAsync(dout->out + static_cast<long long>(i) * h->n_cols, h->d_dense + static_cast<long long>(r) * h->n_cols,
+                                       static_cast<size_t>(h->n_cols) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
           }
         } else {
-          MR_LAUNCH(h, launch_gather_columns(h->d_dense, cn, h->S, dout->d_ids, dout->n_ids, dout->d_out, h->U, b0 + c0, h->stream));
+          MR_LAUNCH(h, launch_gather_columns(h->d_dense, cn, h->n_cols, dout->d_ids, dout->n_ids, dout->d_out, h->U, b0 + c0, h->stream));
         }
         MR_CUDA(h, cudaStreamSynchronize(h->stream));
       }
     } else {
       if (model == MODEL_AGG || model == MODEL_STOCH)
-        MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, b0, nb, h->S, h->d_sel, h->sel_pitch, h->stream));
+        MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, b0, nb, h->n_cols, h->d_sel, h->sel_pitch, h->stream));
       MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, need_ubm ? h->d_sint_u : nullptr, need_ibm ? h->d_sint_i : nullptr, h->spitch,
-                               (model == MODEL_AGG || model == MODEL_STOCH) ? h->d_sel : nullptr, h->sel_pitch, b0, nb, h->S, h->d_rsa,
+                               (model == MODEL_AGG || model == MODEL_STOCH) ? h->d_sel : nullptr, h->sel_pitch, b0, nb, h->n_cols, h->d_rsa,
                                h->d_rsd, k, h->d_out_song, h->d_out_score, h->d_out_len, h->stream));
     }
   }
@@ -718,6 +724,7 @@ int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long
   bp->model = model;
   bp->ubm_int_ok = h->ubm_int_ok ? 1 : 0;
   bp->rsd_up = h->d_rsd_up;
+  bp->te_end = h->d_te_end; bp->song_off = h->win_lo;
   if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
   if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
   if (model == MR_AGG) {
@@ -801,8 +808,33 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   const int T = n_train, S = n_songs;
   const long long nnz = tr_rowptr[T];
   h->T = T; h->S = S; h->nnz_tr = nnz;
+  // song window: rotate the song ids so that the window becomes the columns [0, n_cols) (see mr_handle)
+  if (h->win_hi > S || h->win_lo >= (h->win_hi ? h->win_hi : S)) return fail(h, MR_ERR_BAD_ARG, "song window [%d,%d) outside [0,%d)", h->win_lo, h->win_hi, S);
+  if (h->win_hi == 0) h->win_hi = S;
+  h->windowed = h->win_lo > 0 || h->win_hi < S;
+  h->n_cols = h->win_hi - h->win_lo;
+  std::vector<int32_t> rot_col, rot_deg; std::vector<long long> tr_wend;
+  if (h->windowed) {
+    // the windowed path exists in the item-space formulation with inverted-index counts only
+    if (h->engine == MR_ENGINE_TENSOR || h->space_flag == MR_SPACE_USER)
+      return fail(h, MR_ERR_BAD_ARG, "a song window needs MR_ENGINE_SPARSE / MR_SPACE_ITEM (or AUTO)");
+    h->engine = MR_ENGINE_SPARSE; h->space_flag = MR_SPACE_ITEM;
+    const int lo = h->win_lo, up = S - lo;
+    rot_col.resize(static_cast<size_t>(std::max<long long>(nnz, 1))); tr_wend.resize(T);
+    for (int v = 0; v < T; ++v) {
+      const int32_t* b = tr_col + tr_rowptr[v]; const int32_t* e = tr_col + tr_rowptr[v + 1];
+      const int32_t* m = std::lower_bound(b, e, lo);             // [b, m) < lo <= [m, e)
+      int32_t* o = rot_col.data() + tr_rowptr[v];
+      for (const int32_t* p = m; p < e; ++p) *o++ = *p - lo;
+      for (const int32_t* p = b; p < m; ++p) *o++ = *p + up;
+      tr_wend[v] = tr_rowptr[v] + (std::lower_bound(m, e, h->win_hi) - m);
+    }
+    rot_deg.resize(S);
+    for (int s = 0; s < S; ++s) rot_deg[s < lo ? s + up : s - lo] = deg_song_all[s];
+    tr_col = rot_col.data(); deg_song_all = rot_deg.data();
+  }
   h->pitchS = round_up(S, 128); h->pitchT = round_up(T, 128);
-  h->spitch = round_up(S, 32); h->ldg = round_up(S, 32);
+  h->spitch = round_up(h->n_cols, 32); h->ldg = round_up(S, 32);
   h->deg_song.assign(deg_song_all, deg_song_all + S);
   h->deg_song_train.assign(S, 0);
   for (long long i = 0; i < nnz; ++i) h->deg_song_train[tr_col[i]]++;
@@ -844,6 +876,12 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<long long> trp(tr_rowptr, tr_rowptr + T + 1);
   if ((rc = dev_upload(h, &h->d_tr_ptr, trp.data(), trp.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_tr_col, tr_col, static_cast<size_t>(nnz), h->allocs))) return rc;
+  h->d_tr_end = h->d_tr_ptr + 1;
+  if (h->windowed) {
+    long long* d_end = nullptr;
+    if ((rc = dev_upload(h, &d_end, tr_wend.data(), tr_wend.size(), h->allocs))) return rc;
+    h->d_tr_end = d_end;
+  }
   if ((rc = dev_upload(h, &h->d_csc_ptr, csc_ptr.data(), csc_ptr.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_csc_idx, csc_idx.data(), static_cast<size_t>(nnz), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_qv, qv.data(), qv.size(), h->allocs))) return rc;
@@ -895,7 +933,7 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   if (const char* e = getenv("MRSCORE_HEAD_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) h->head_threads = t; }
   h->n_groups = h->num_sms * std::min(32, kHeadCtasPerSm * 256 / h->head_threads);   // one wave of resident CTAs = one song tile for the whole batch
   if (const char* e = getenv("MRSCORE_HEAD_GROUPS")) h->n_groups = std::max(1, atoi(e));   // test aid: few groups -> several users per group on small shards
-  h->sel_pitch = (S + 63) / 64;
+  h->sel_pitch = (h->n_cols + 63) / 64;
   // item-space head: songs with enough train listeners that a dense precomputed row beats expanding them per test user
   {
     long long min_deg = std::max<long long>(2, S / 6000);   // below ~64 listeners expanding a song on the fly is cheaper than streaming its row
@@ -971,6 +1009,23 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   }
   h->pair_index_base = pair_index_base;
   h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
+  std::vector<long long> te_wend;
+  if (h->windowed) {
+    // rotate the rows like the train rows (mr_load); the pair index of column c of user u in MAIN:57-59 order is
+    // pair_base[u] + (c + win_lo) - (listened songs below win_lo) - (listened songs of the window below c): fold the constants into pair_base
+    const int lo = h->win_lo, up = h->S - lo;
+    te_wend.resize(U);
+    for (int u = 0; u < U; ++u) {
+      const int32_t* b = te_col + te_rowptr[u]; const int32_t* e = te_col + te_rowptr[u + 1];
+      const int32_t* m = std::lower_bound(b, e, lo);
+      int32_t* o = h->h_te_col.data() + te_rowptr[u];
+      for (const int32_t* p = m; p < e; ++p) *o++ = *p - lo;
+      for (const int32_t* p = b; p < m; ++p) *o++ = *p + up;
+      te_wend[u] = te_rowptr[u] + (std::lower_bound(m, e, h->win_hi) - m);
+      pair_base[u] += lo - (m - b);
+    }
+    te_col = h->h_te_col.data();
+  }
   // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it — only the
   // tensor engine's user-space IBM path consumes them
   const int n_batches = (U + kUserBatch - 1) / kUserBatch;
@@ -991,6 +1046,12 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   }
   lap("host arrays");
   if ((rc = slot_upload(h, mr_handle::SL_TE_PTR, &h->d_te_ptr, h->h_te_ptr.data(), h->h_te_ptr.size()))) return rc;
+  h->d_te_end = h->d_te_ptr + 1;
+  if (h->windowed) {
+    long long* d_end = nullptr;
+    if ((rc = slot_upload(h, mr_handle::SL_TE_END, &d_end, te_wend.data(), te_wend.size()))) return rc;
+    h->d_te_end = d_end;
+  }
   if ((rc = slot_upload(h, mr_handle::SL_TE_COL, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz)))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_TE_GROW, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz)))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_RSA, &h->d_rsa, rsa.data(), rsa.size()))) return rc;
@@ -1252,9 +1313,9 @@ int mr_score_dense(mr_handle* h, int model, double* out_UxS) {
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "mr_score_dense: model must be MR_UBM or MR_IBM");
   if (!out_UxS) return fail(h, MR_ERR_BAD_ARG, "null output");
-  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->S))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->n_cols))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
-  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
+  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model; bp.te_end = h->d_te_end; bp.song_off = h->win_lo;
   DenseOut dout{DenseOut::ALL, out_UxS, nullptr, 0, nullptr, nullptr};
   return run_batches(h, model, bp, 0, RUN_DENSE, &dout);
 }
@@ -1264,18 +1325,20 @@ static int score_subset(mr_handle* h, int model, const int32_t* ids, int n, doub
   if (rc) return rc;
   if (model != MR_UBM && model != MR_IBM) return fail(h, MR_ERR_BAD_ARG, "model must be MR_UBM or MR_IBM");
   if (n < 0 || (n > 0 && (!ids || !out))) return fail(h, MR_ERR_BAD_ARG, "null id list / output");
-  const int limit = songs ? h->S : h->U;
+  const int first = songs ? h->win_lo : 0, limit = songs ? h->win_lo + h->n_cols : h->U;   // songs: the scored columns (the window, if one is set)
   for (int i = 0; i < n; ++i)
-    if (ids[i] < 0 || ids[i] >= limit) return fail(h, MR_ERR_BAD_ARG, "%s id %d out of range [0,%d)", songs ? "song" : "test user", ids[i], limit);
+    if (ids[i] < first || ids[i] >= limit) return fail(h, MR_ERR_BAD_ARG, "%s id %d out of range [%d,%d)", songs ? "song" : "test user", ids[i], first, limit);
   if (n == 0) return MR_OK;
-  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->S))) return rc;
+  if ((rc = slot_alloc(h, mr_handle::SL_DENSE, &h->d_dense, static_cast<size_t>(std::min(h->batch_rows, kDenseChunk)) * h->n_cols))) return rc;
   if (model == MR_IBM && h->engine != MR_ENGINE_SPARSE && (rc = ensure_gram_ws(h, h->max_batch_rows))) return rc;
-  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model;
+  BlendParams bp; memset(&bp, 0, sizeof bp); bp.model = model; bp.te_end = h->d_te_end; bp.song_off = h->win_lo;
   std::vector<void*> tmp;
   DenseOut dout{songs ? DenseOut::SONGS : DenseOut::USERS, out, ids, n, nullptr, nullptr};
   if (songs) {
     int* d_ids = nullptr;
-    if ((rc = dev_upload(h, &d_ids, ids, static_cast<size_t>(n), tmp)) || (rc = dev_alloc(h, &dout.d_out, static_cast<size_t>(n) * h->U, tmp))) { free_list(tmp); return rc; }
+    std::vector<int> cols(ids, ids + n);
+    for (int& c : cols) c -= h->win_lo;
+    if ((rc = dev_upload(h, &d_ids, cols.data(), static_cast<size_t>(n), tmp)) || (rc = dev_alloc(h, &dout.d_out, static_cast<size_t>(n) * h->U, tmp))) { free_list(tmp); return rc; }
     dout.d_ids = d_ids;
   }
   rc = run_batches(h, model, bp, 0, RUN_DENSE, &dout);
@@ -1346,6 +1409,12 @@ int mr_set_option(mr_handle* h, int option, int64_t value) {
       if (h->loaded) return fail(h, MR_ERR_STATE, "MR_OPT_HEAD_MIN_DEG must be set before mr_load (it selects the head songs)");
       if (value < 0) return fail(h, MR_ERR_BAD_ARG, "MR_OPT_HEAD_MIN_DEG must be >= 0");
       h->opt_head_min_deg = value;
+      return MR_OK;
+    case MR_OPT_SONG_WINDOW_LO:
+    case MR_OPT_SONG_WINDOW_HI:
+      if (h->loaded) return fail(h, MR_ERR_STATE, "the song window must be set before mr_load (ids are rotated and the head rows sized by it)");
+      if (value < 0 || value > 0x7fffffff) return fail(h, MR_ERR_BAD_ARG, "song window bound out of range");
+      (option == MR_OPT_SONG_WINDOW_LO ? h->win_lo : h->win_hi) = static_cast<int>(value);
       return MR_OK;
     case MR_OPT_ITEM_BATCH:
       if (value < 0) return fail(h, MR_ERR_BAD_ARG, "MR_OPT_ITEM_BATCH must be >= 0");
@@ -1502,6 +1571,24 @@ int mr_topk_packed(mr_handle* h, int k, void** base, uint64_t* bytes, uint64_t* 
   return MR_OK;
 }
 
+int mr_topk_merge(mr_handle* h, int k, int n_parts, int n_users, const int32_t* const* part_song, const double* const* part_score,
+                  const int32_t* const* part_len, int32_t* out_song, double* out_score, int32_t* out_len) {
+  if (!h || !h->stream) return MR_ERR_STATE;
+  if (k < 1 || k > 1024 || n_users < 0 || !part_song || !part_score || !part_len || !out_song || !out_score || !out_len)
+    return fail(h, MR_ERR_BAD_ARG, "mr_topk_merge: null argument or k outside [1,1024]");
+  if (n_parts < 1 || n_parts > kMergeMaxParts) return fail(h, MR_ERR_BAD_ARG, "mr_topk_merge: %d partitions (1..%d)", n_parts, kMergeMaxParts);
+  MergeParts p; memset(&p, 0, sizeof p);
+  p.n = n_parts;
+  for (int i = 0; i < n_parts; ++i) {
+    if (!part_song[i] || !part_score[i] || !part_len[i]) return fail(h, MR_ERR_BAD_ARG, "mr_topk_merge: partition %d has a null array", i);
+    p.song[i] = part_song[i]; p.score[i] = part_score[i]; p.len[i] = part_len[i];
+  }
+  MR_CUDA(h, cudaSetDevice(h->device));
+  PhaseTimer t(h, MR_T_TOPK);
+  MR_LAUNCH(h, launch_merge_topk(p, k, n_users, out_song, out_score, out_len, h->stream));
+  return MR_OK;
+}
+
 int mr_topk(mr_handle* h, int model, double param, uint64_t seed, int k, int32_t* out_song, double* out_score, int32_t* out_len) {
   if (!out_song || !out_score || !out_len) return fail(h, MR_ERR_BAD_ARG, "null output");
   const TopkHostOut ho{out_song, out_score, out_len};
@@ -1520,10 +1607,10 @@ int mr_reset_timing(mr_handle* h) {
 }
 int mr_get_info(mr_handle* h, int64_t* out, int n) {
   if (!h || !out) return MR_ERR_BAD_ARG;
-  const int64_t v[14] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
+  const int64_t v[16] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
                          h->n_head_entries, h->n_tail_entries, h->n_ex, h->batch_rows, h->n_groups,
-                         h->h_split_ptr.empty() ? 0 : h->h_split_ptr.back()};
-  for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
+                         h->h_split_ptr.empty() ? 0 : h->h_split_ptr.back(), h->n_cols, h->win_lo};
+  for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
   return MR_OK;
 }
 int mr_prepare(mr_handle* h) {

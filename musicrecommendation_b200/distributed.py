@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process per GPU, test users sharded, no data-path collective.
+"""Multi-GPU plumbing: one process per GPU; test users sharded with no data-path collective, or songs partitioned with one all-to-all.
 
 The reference distributes the same way (distributed.scala:450-452: `ctx.parallelize(testUsers, slices).map(getRanks1).collect`):
 every worker holds the whole train set (there: the task closure; here: a train replica in each GPU's HBM) and scores a
@@ -101,6 +101,41 @@ def gather_topk_packed(mr, k: int, world: int, rank: int, lib_stream, comm_strea
         dist.gather(st["stage"], gather_list=bufs, dst=dst)
     lib_stream.wait_event(st["copied"])
     return bufs
+
+
+def song_window(n_songs: int, rank: int, world: int) -> tuple[int, int]:
+    """Song partition of `rank` (the reference's second partitioning, distributed.scala:459-461: `ctx.parallelize(songs, n)`): a contiguous,
+    balanced range of song ids.  A handle created with this window scores ALL test users against its songs only."""
+    return shard_range(n_songs, rank, world)
+
+
+_EXCHANGE: dict = {}
+
+
+def exchange_song_partitions(song, score, length, n_users_total: int, world: int, rank: int, group=None):
+    """Song partitioning's exchange step: every rank holds, for ALL test users, the ranked list of its own song window; afterwards rank r
+    holds all `world` lists of the users of ITS test-user range (shard_range): one all-to-all per array (row blocks of unequal size
+    allowed).  Returns (parts_song [world, n_r, k], parts_score [world, n_r, k], parts_len [world, n_r]); the receive buffers are reused
+    by the next call with the same shapes.  Tensors live where the backend needs them (CUDA for nccl, CPU for gloo)."""
+    import torch
+    import torch.distributed as dist
+    song, score, length = torch.as_tensor(song), torch.as_tensor(score), torch.as_tensor(length)
+    ranges = [shard_range(n_users_total, r, world) for r in range(world)]
+    n_mine = ranges[rank][1] - ranges[rank][0]
+    send_rows = [b - a for a, b in ranges]
+    outs = []
+    for t in (song, score, length):
+        shape = (world, n_mine) + tuple(t.shape[1:])
+        key = (str(t.device), t.dtype, shape)
+        recv = _EXCHANGE.get(key)
+        if recv is None:
+            recv = _EXCHANGE[key] = torch.empty(shape, dtype=t.dtype, device=t.device)
+        if world == 1:
+            recv[0].copy_(t)
+        else:
+            dist.all_to_all_single(recv.view((world * n_mine,) + tuple(t.shape[1:])), t.contiguous(), [n_mine] * world, send_rows, group=group)
+        outs.append(recv)
+    return tuple(outs)
 
 
 def split_train_users(ds: Dataset, rank: int, world: int) -> Dataset:

@@ -175,7 +175,9 @@ class MusicRecommender:
 
     def __init__(self, trainFile, testFile=None, testLabelsFile=None, device: int = 0, engine: int = _lib.MR_ENGINE_AUTO,
                  profile: bool = False, space: int = _lib.MR_SPACE_AUTO, ingest: str = "host", head_min_deg: int = 0,
-                 item_batch: int = 0):
+                 item_batch: int = 0, song_window=None):
+        """song_window = (lo, hi): score only the songs [lo, hi) of every test user — one song partition of distributed.scala:459-461
+        (MR_OPT_SONG_WINDOW_*): dense models become [U, hi - lo], getTopK ranks inside the window (global song ids)."""
         if isinstance(trainFile, Dataset):
             ds = trainFile
         elif ingest == "native":
@@ -194,6 +196,10 @@ class MusicRecommender:
             self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_HEAD_MIN_DEG, int(head_min_deg)))
         if item_batch:
             self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_ITEM_BATCH, int(item_batch)))
+        self.song_window = (0, ds.S) if song_window is None else (int(song_window[0]), int(song_window[1]))
+        if song_window is not None:
+            self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_SONG_WINDOW_LO, self.song_window[0]))
+            self._check(self._lib.mr_set_option(self._h, _lib.MR_OPT_SONG_WINDOW_HI, self.song_window[1]))
         a = self._arrs = dict(
             tr_ptr=np.ascontiguousarray(ds.tr_ptr, np.int64), tr_col=np.ascontiguousarray(ds.tr_col, np.int32),
             te_ptr=np.ascontiguousarray(ds.te_ptr, np.int64), te_col=np.ascontiguousarray(ds.te_col, np.int32),
@@ -243,9 +249,11 @@ class MusicRecommender:
         self.ds = ds_shard
 
     def _model(self, kind: int, name: str) -> Model:
-        out = np.empty((self.ds.U, self.ds.S), np.float64)
+        lo, hi = self.song_window
+        out = np.empty((self.ds.U, hi - lo), np.float64)
         self._check(self._lib.mr_score_dense(self._h, kind, _p(out)))
-        return Model(out, self.ds.test_users, self.ds.songs, name)
+        songs = self.ds.songs if (lo, hi) == (0, self.ds.S) or self.ds.songs is None else self.ds.songs[lo:hi]
+        return Model(out, self.ds.test_users, songs, name)
 
     # ------------------------------------------------------------------ reference method surface
     def getUserBasedModel(self) -> Model:                    # MR:132
@@ -311,7 +319,7 @@ class MusicRecommender:
         """DIST UserBasedModel/ItemBasedModel.getRanks1(user) (DIST:198-205, 269-276) for the listed test users of the current shard:
         [len(users), S] fp64, NaN at listened pairs."""
         ids = np.ascontiguousarray(users, np.int32)
-        out = np.empty((len(ids), self.ds.S), np.float64)
+        out = np.empty((len(ids), self.song_window[1] - self.song_window[0]), np.float64)
         self._check(self._lib.mr_score_users(self._h, model, _p(ids), len(ids), _p(out)))
         return out
 
@@ -322,13 +330,14 @@ class MusicRecommender:
         self._check(self._lib.mr_score_songs(self._h, model, _p(ids), len(ids), _p(out)))
         return out
 
-    def mapAtK(self, k: int = 500, top=None, per_user: bool = False):
+    def mapAtK(self, k: int = 500, top=None, per_user: bool = False, labels: Dataset | None = None):
         """mAP@k (north_star's mAP@500; MSD-challenge definition, include/mrscore.h) of ranked lists against this data set's label rows.
         top = (song [U,k], len [U]) as getTopK returns them, or None for the device-resident result of the last getTopK / mr_topk_device."""
-        lp = np.ascontiguousarray(self.ds.lab_ptr, np.int64)
-        lc = np.ascontiguousarray(self.ds.lab_col, np.int32)
+        lab = labels if labels is not None else self.ds      # labels: the data set whose label rows match explicit lists of other users
+        lp = np.ascontiguousarray(lab.lab_ptr, np.int64)
+        lc = np.ascontiguousarray(lab.lab_col, np.int32)
         out = C.c_double(0.0)
-        ap = np.zeros(self.ds.U, np.float64)
+        ap = np.zeros(lab.U, np.float64)
         if top is None:
             self._check(self._lib.mr_map_at_k(self._h, k, None, None, self.ds.U, _p(lp), _p(lc), C.byref(out), _p(ap)))
         else:
@@ -349,6 +358,15 @@ class MusicRecommender:
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
         return (torch.as_tensor(_Arr(ps.value, (U, k), "<i4"), device="cuda"), torch.as_tensor(_Arr(pv.value, (U, k), "<f8"), device="cuda"),
                 torch.as_tensor(_Arr(pl.value, (U,), "<i4"), device="cuda"))
+
+    def mergeTopK(self, parts_song, parts_score, parts_len, out_song, out_score, out_len):
+        """Join the ranked lists of several song partitions for the same users (mr_topk_merge; the `.collect` + ranking of
+        distributed.scala:459-461).  All arguments are CUDA torch tensors: parts_* [P, n, k] / [P, n], out_* [n, k] / [n]; the join runs
+        on the library stream."""
+        P, n, k = parts_song.shape
+        tab = lambda t: (C.c_void_p * P)(*[t[i].data_ptr() for i in range(P)])      # noqa: E731
+        self._check(self._lib.mr_topk_merge(self._h, k, P, n, tab(parts_song), tab(parts_score), tab(parts_len), C.c_void_p(out_song.data_ptr()),
+                                            C.c_void_p(out_score.data_ptr()), C.c_void_p(out_len.data_ptr())))
 
     def topk_packed_tensor(self, k: int):
         """The last top-k result as ONE uint8 torch view of device memory plus the byte offsets of its parts:
@@ -432,10 +450,10 @@ class MusicRecommender:
         return dict(zip(_lib.TIMING_NAMES, list(t)))
 
     def info(self) -> dict:
-        v = (C.c_int64 * 14)()
-        self._lib.mr_get_info(self._h, v, 14)
+        v = (C.c_int64 * 16)()
+        self._lib.mr_get_info(self._h, v, 16)
         return dict(zip(["engine", "launches", "dense_bytes", "n_items", "num_sms", "device_bytes", "space", "n_head", "head_entries",
-                         "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users"], list(v)))
+                         "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users", "n_cols", "win_lo"], list(v)))
 
     # ------------------------------------------------------------------ model file I/O (MR:489-512)
     def writeModelOnFile(self, model: Model, outputFileName: str = "") -> int:

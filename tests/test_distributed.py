@@ -16,7 +16,21 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from musicrecommendation_b200.dataset import synth
-from musicrecommendation_b200.distributed import shard_range, pair_index_bases, gather_topk, split_train_users, reduce_scatter_rows
+from musicrecommendation_b200.distributed import (shard_range, pair_index_bases, gather_topk, split_train_users, reduce_scatter_rows, song_window,
+                                                  exchange_song_partitions)
+
+
+def merge_lists_host(parts_song, parts_score, parts_len, k):
+    """Checker for the join of the song partitions' ranked lists (on the GPU: mr_topk_merge): score descending, song id ascending."""
+    P, n, _ = parts_song.shape
+    song = np.full((n, k), -1, np.int32); score = np.zeros((n, k)); ln = np.zeros(n, np.int32)
+    for u in range(n):
+        cand = [(-float(parts_score[p, u, i]), int(parts_song[p, u, i])) for p in range(P) for i in range(int(parts_len[p, u]))]
+        cand.sort()
+        ln[u] = min(k, len(cand))
+        for i, (neg, sg) in enumerate(cand[:k]):
+            song[u, i], score[u, i] = sg, -neg
+    return song, score, ln
 
 
 def _free_port():
@@ -54,6 +68,15 @@ def _worker(rank, world, port, out_dir):
     part = torch.from_numpy(oracle.gram_rows(split_train_users(ds, rank, world), np.arange(0, 64)))
     mine = reduce_scatter_rows(part, world, rank)
     np.save(os.path.join(out_dir, f"gram_rows_rank{rank}.npy"), mine.numpy())
+    # song partitioning (DIST:459-461): every rank ranks ALL users inside its song window, one all-to-all hands rank r every window's
+    # lists of ITS users, the join gives their global top-k
+    lo, hi = song_window(ds.S, rank, world)
+    full_ubm = oracle.canon_scores(ds, oracle.UBM)
+    wsong, wscore, wlen = oracle.topk(np.ascontiguousarray(full_ubm[:, lo:hi]), 50)
+    wsong = np.where(wsong >= 0, wsong + lo, wsong).astype(np.int32)
+    for _ in range(2):          # the second call reuses the receive buffers
+        ps, pv, pl = exchange_song_partitions(wsong, wscore, wlen, ds.U, world, rank)
+    np.savez(os.path.join(out_dir, f"partition_join_rank{rank}.npz"), **dict(zip(("song", "score", "len"), merge_lists_host(ps.numpy(), pv.numpy(), pl.numpy(), 50))))
     if rank == 0:
         np.savez(os.path.join(out_dir, "gathered.npz"), **{f"{k}_{i}": v for k, vs in results.items() for i, v in enumerate(vs)})
     dist.barrier()
@@ -80,6 +103,12 @@ def test_two_process_gloo_gather_matches_single_process(tmp_path, oracle_lib):
     for r in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / f"gram_rows_rank{r}.npy"), full[r * 32:(r + 1) * 32])
     ws, wv, wl = oracle_lib.topk(ubm, 50)
+    for r in range(world):
+        u0, u1 = shard_range(ds.U, r, world)
+        j = np.load(tmp_path / f"partition_join_rank{r}.npz")
+        np.testing.assert_array_equal(j["song"], ws[u0:u1])
+        np.testing.assert_array_equal(j["score"], wv[u0:u1])
+        np.testing.assert_array_equal(j["len"], wl[u0:u1])
     pick = np.r_[0:5, 6:11]                      # shard_range(11, r, 2) = [0,6), [6,11)
     np.testing.assert_array_equal(got["eq_0"], ws[pick])
     np.testing.assert_array_equal(got["eq_1"], wv[pick])
