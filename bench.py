@@ -271,6 +271,9 @@ def main():
     ap.add_argument("--partition", default="auto", choices=["auto", "users", "songs"],
                     help="msd on N > 1 GPUs: shard the test users (DIST:450-452) or partition the songs (DIST:459-461; auto = songs: the head-row "
                          "precompute is divided by N instead of replicated)")
+    ap.add_argument("--emulate-song-partition", default="", metavar="R/N",
+                    help="profiling aid on ONE GPU (not a bench line): score all test users against song partition R of N, i.e. what one GPU of an "
+                         "N-GPU song-partitioned job computes, without the exchange")
     ap.add_argument("--batch-users", type=int, default=0, help="MR_OPT_ITEM_BATCH: cap on test users per batch (0: as many as fit in HBM)")
     ap.add_argument("--ksplit-songs", type=int, nargs="+", default=[20000])
     ap.add_argument("--ksplit-mode", default="auto", choices=["auto", "fused", "nccl"])
@@ -316,6 +319,10 @@ def main():
     by_songs = msd and world > 1 and args.partition in ("auto", "songs") and n_job_users % world == 0    # equal user ranges: one gather of equal blocks
     ds, desc, total_pairs = make_workload(args.workload, rank, world, args.users, "songs" if by_songs else "users")
     window = song_window(ds.S, rank, world) if by_songs else None
+    if args.emulate_song_partition and world == 1:
+        r_emu, n_emu = (int(x) for x in args.emulate_song_partition.split("/"))
+        window = song_window(ds.S, r_emu, n_emu)
+        desc += f" [EMULATION: song partition {r_emu} of {n_emu} only, no exchange — not a bench line]"
     my_u0, my_u1 = shard_range(ds.U, rank, world) if by_songs else (0, ds.U)     # the users whose joined lists this rank ends up with
     engine = {"auto": _lib.MR_ENGINE_AUTO, "tensor": _lib.MR_ENGINE_TENSOR, "sparse": _lib.MR_ENGINE_SPARSE}[args.engine]
     space = {"auto": _lib.MR_SPACE_AUTO, "user": _lib.MR_SPACE_USER, "item": _lib.MR_SPACE_ITEM}[args.space]
@@ -325,7 +332,7 @@ def main():
         # measured on one B200 (gpurun_out/r02_bench_u13750_md*.json): per 13 750-user batch the step costs 88.7 / 89.7 / 100.3 / 129.7 ms and the
         # precompute 130 / 113 / 57 / 35 ms at min_deg 64 / 150 / 400 / 1000 — few batches per GPU favour a small head
         batches = -(-ds.U // 13750)
-        head_min_deg = 0 if by_songs else ((400 if batches <= 5 else 150) if msd else 0)
+        head_min_deg = 0 if (by_songs or window) else ((400 if batches <= 5 else 150) if msd else 0)
     t_load0 = time.perf_counter()
     mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space, head_min_deg=head_min_deg, item_batch=args.batch_users, song_window=window)
     lib, h = mr._lib, mr._h

@@ -305,18 +305,20 @@ int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, co
 // Work is the flattened list of (tail entry, listener) pairs (tu_lptr = exclusive prefix of the entries' train degrees): one
 // warp per pair, lanes over I_v, exact u64 atomics (fire-and-forget).  Flattening keeps all 64 warp slots of every SM busy
 // although entries have between 1 and a few hundred listeners.
+// kLanes: lanes that share one pair.  32 for whole rows; with a song window only the in-window prefix of I_v is walked (a few songs
+// of ~47 when the window is 1/8 of the songs), so a pair gets 8 or 16 lanes and a warp works on 4 or 2 pairs at a time.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kModels>
+template <int kModels, int kLanes>
 __global__ void __launch_bounds__(256)
 tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_song, const long long* __restrict__ tu_lptr,
                     long long e0, long long e1, const long long* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
                     const long long* __restrict__ tr_ptr, const long long* __restrict__ tr_end, const int* __restrict__ tr_col,
                     const uint32_t* __restrict__ qv, const uint32_t* __restrict__ qd, int u0, long long* __restrict__ sint_u,
                     long long* __restrict__ sint_i, long long spitch) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & (kLanes - 1);
   const long long w0 = tu_lptr[e0], w1 = tu_lptr[e1];
-  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long w = w0 + static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); w < w1; w += n_warps) {
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x / kLanes);
+  for (long long w = w0 + static_cast<long long>(blockIdx.x) * (blockDim.x / kLanes) + (threadIdx.x / kLanes); w < w1; w += n_warps) {
     long long lo = e0, hi = e1;                      // e = upper_bound(tu_lptr, w) - 1 within [e0, e1)
     while (lo < hi) { const long long m = (lo + hi) >> 1; if (tu_lptr[m + 1] <= w) lo = m + 1; else hi = m; }
     const long long e = lo;
@@ -327,7 +329,7 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
     unsigned long long* su = reinterpret_cast<unsigned long long*>(sint_u) + static_cast<long long>(b) * spitch;
     unsigned long long* si = reinterpret_cast<unsigned long long*>(sint_i) + static_cast<long long>(b) * spitch;
     const long long rb = tr_ptr[v], re = tr_end[v];
-    for (long long m = rb + lane; m < re; m += 32) {
+    for (long long m = rb + lane; m < re; m += kLanes) {
       const int s = __ldg(tr_col + m);
       if (s == j) continue;
       if (kModels & 1) atomicAdd(su + s, q);
@@ -339,14 +341,18 @@ tail_scatter_kernel(const int* __restrict__ tu_user, const int* __restrict__ tu_
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const long long* tr_end, const int* tr_col,
                         const uint32_t* qv, const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs,
-                        cudaStream_t st) {
+                        int lanes, cudaStream_t st) {
   if (e1 <= e0 || n_pairs <= 0) return 0;
-  // one warp per (entry, listener) pair in short-lived CTAs (measured 25 % faster than a persistent grid-stride grid: the block
-  // scheduler balances the 1..4000-song listeners better than a static stride does)
-  const int grid = static_cast<int>(std::min<long long>((n_pairs + 7) / 8, 1LL << 30));
-  if (models == 1) tail_scatter_kernel<1><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else if (models == 2) tail_scatter_kernel<2><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
-  else tail_scatter_kernel<3><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch);
+  if (lanes != 8 && lanes != 16 && lanes != 32) return -2;
+  // one warp (or 8 / 16 lanes of one) per (entry, listener) pair in short-lived CTAs (measured 25 % faster than a persistent
+  // grid-stride grid: the block scheduler balances the 1..4000-song listeners better than a static stride does)
+  const int per_cta = 256 / lanes;
+  const int grid = static_cast<int>(std::min<long long>((n_pairs + per_cta - 1) / per_cta, 1LL << 30));
+#define MR_TS(M, L) tail_scatter_kernel<M, L><<<grid, 256, 0, st>>>(tu_user, tu_song, tu_lptr, e0, e1, csc_ptr, csc_idx, tr_ptr, tr_end, tr_col, qv, qd, u0, sint_u, sint_i, spitch)
+#define MR_TS_L(M) do { if (lanes == 32) MR_TS(M, 32); else if (lanes == 16) MR_TS(M, 16); else MR_TS(M, 8); } while (0)
+  if (models == 1) MR_TS_L(1); else if (models == 2) MR_TS_L(2); else MR_TS_L(3);
+#undef MR_TS_L
+#undef MR_TS
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

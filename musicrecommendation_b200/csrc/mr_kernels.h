@@ -88,7 +88,7 @@ int launch_head_fixup(int models, const long long* hu_ptr, const int* hu_row, co
 int launch_tail_scatter(int models, const int* tu_user, const int* tu_song, const long long* tu_lptr, long long e0, long long e1,
                         const long long* csc_ptr, const int* csc_idx, const long long* tr_ptr, const long long* tr_end, const int* tr_col,
                         const uint32_t* qv, const uint32_t* qd, int u0, long long* sint_u, long long* sint_i, long long spitch, long long n_pairs,
-                        cudaStream_t st);
+                        int lanes, cudaStream_t st);
 
 // ---- per-shard work lists of the item-space engine, built on the device (k7_testlists.cu)
 size_t test_lists_temp_bytes(long long nnz);

@@ -82,7 +82,7 @@ struct mr_handle {
   int U = 0; long long nnz_te = 0; bool have_test = false;
   // grow-only device buffers of the test shard and its results: steady-state mr_set_test_users / mr_topk calls do no cudaMalloc
   enum { SL_TE_PTR, SL_TE_COL, SL_TE_GROW, SL_RSA, SL_RSA_F, SL_PAIR_BASE, SL_ROWS, SL_HU_PTR, SL_HU_ROW, SL_HU_SONG, SL_HU_Q, SL_TU_USER,
-         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_EX_PTR, SL_EX_SONG, SL_EX_G, SL_EX_GQ, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_PACK, SL_TE_END, SL_N };
+         SL_TU_SONG, SL_TU_LPTR, SL_TU_PTR, SL_EX_PTR, SL_EX_SONG, SL_EX_G, SL_EX_GQ, SL_L_FLAG, SL_L_HEADPOS, SL_L_DEG, SL_L_LSUM, SL_L_TMP, SL_COPY_DESC, SL_SEG, SL_GRP_HDR, SL_GE_ROW, SL_GE_Q, SL_SPLIT_ROWS, SL_SINT_U, SL_SINT_I, SL_SEL, SL_GRAM_IDS, SL_CNT, SL_SIMF, SL_DENSE, SL_OUT_PACK, SL_TE_END, SL_PRE_G, SL_PRE_GQ, SL_PRE_EXC, SL_N };
   void* slot_p[SL_N] = {}; size_t slot_cap[SL_N] = {};
   long long *d_te_ptr = nullptr, *d_pair_base = nullptr; int *d_te_col = nullptr, *d_te_grow = nullptr; double* d_rsa = nullptr; float* d_rsa_f = nullptr;
   std::vector<long long> h_te_ptr; std::vector<int> h_te_col;
@@ -336,14 +336,26 @@ int ensure_head_rows(mr_handle* h) {
     chunk = std::max<long long>(4, std::min<long long>((64LL << 20) / (h->spitch * (packed ? 8 : 12)), 4096));
     if (const char* e = getenv("MRSCORE_PRECOMPUTE_CHUNK")) chunk = std::max(1LL, atoll(e));
   }
+  // The staging rows and the exception list live in grow-only slots of the handle: a rebuild (mr_invalidate_prepared + mr_prepare, i.e.
+  // every step of a job that counts the model build) does no cudaMalloc / cudaFree — next to 100+ GB of live allocations those cost
+  // tens to hundreds of milliseconds, more than the kernels of a song partition's precompute.  Only the tensor engine's dense operands
+  // (small shapes) are temporary.
   std::vector<void*> tmp;
   uint32_t* g_stage = nullptr; unsigned long long* gq_stage = nullptr;
   HeadExceptions ex{};
   ex.capacity = n_staged > 0 ? (1u << 24) : 1u;
   const size_t stage_entries = n_staged > 0 ? static_cast<size_t>(chunk) * h->spitch : 1;
-  if ((rc = dev_alloc(h, &g_stage, packed ? 1 : stage_entries, tmp)) || (rc = dev_alloc(h, &gq_stage, stage_entries, tmp)) ||
-      (rc = dev_alloc(h, &ex.count, 1, tmp)) || (rc = dev_alloc(h, &ex.row, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.song, ex.capacity, tmp)) ||
-      (rc = dev_alloc(h, &ex.g_extra, ex.capacity, tmp)) || (rc = dev_alloc(h, &ex.gq_extra, ex.capacity, tmp))) { free_list(tmp); return rc; }
+  {
+    char* xb = nullptr;                 // [count (16 B)] [gq_extra u64] [row i32] [song i32] [g_extra u32]
+    const size_t cap = ex.capacity;
+    if ((rc = slot_alloc(h, mr_handle::SL_PRE_G, &g_stage, packed ? 1 : stage_entries, true)) ||
+        (rc = slot_alloc(h, mr_handle::SL_PRE_GQ, &gq_stage, stage_entries, true)) || (rc = slot_alloc(h, mr_handle::SL_PRE_EXC, &xb, 16 + cap * 20, true))) return rc;
+    ex.count = reinterpret_cast<unsigned int*>(xb);
+    ex.gq_extra = reinterpret_cast<unsigned long long*>(xb + 16);
+    ex.row = reinterpret_cast<int*>(xb + 16 + cap * 8);
+    ex.song = reinterpret_cast<int*>(xb + 16 + cap * 12);
+    ex.g_extra = reinterpret_cast<uint32_t*>(xb + 16 + cap * 16);
+  }
   auto bail = [&](int code) { cudaStreamSynchronize(h->stream); free_list(tmp); return code; };
   cudaError_t e = cudaMemsetAsync(ex.count, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
@@ -505,14 +517,59 @@ int plan_item_batches_once(mr_handle* h, const std::vector<long long>& hu_ptr, i
       split_rows.push_back(b);
     }
     h->h_split_ptr.push_back(static_cast<int>(split_rows.size()));
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.e1 - a.e0 > b.e1 - b.e0; });
+    // Longest-first packing into G bins of equal cost.  Heavy items (more than 1/8 of a bin's share: a percent of the users) go through
+    // the classic LPT heap; the bulk of light items then tops every bin up to the common level T* (sum over bins of max(0, T* - heavy
+    // load) = light cost) in one sequential sweep with cumulative rounding — O(items) instead of a heap operation per user, which at
+    // 110 000 users per shard was half of mr_set_test_users.
+    {   // counting sort by length, descending, stable
+      int max_n = 0;
+      for (const Item& it : items) max_n = std::max(max_n, it.e1 - it.e0);
+      std::vector<int> start(static_cast<size_t>(max_n) + 2, 0);
+      for (const Item& it : items) start[max_n - (it.e1 - it.e0) + 1]++;
+      for (int i = 0; i <= max_n; ++i) start[i + 1] += start[i];
+      std::vector<Item> sorted(items.size());
+      for (const Item& it : items) sorted[start[max_n - (it.e1 - it.e0)]++] = it;
+      items.swap(sorted);
+    }
     for (auto& v : bins) v.clear();
-    std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> heap;
-    for (int g = 0; g < G; ++g) heap.push({0, g});
-    for (size_t i = 0; i < items.size(); ++i) {
-      auto top = heap.top(); heap.pop();
-      bins[top.second].push_back(static_cast<int>(i));
-      heap.push({top.first + (items[i].e1 - items[i].e0) + kRowCost, top.second});
+    std::vector<long long> load(G, 0);
+    size_t n_heavy = 0;
+    while (n_heavy < items.size() && 8LL * (items[n_heavy].e1 - items[n_heavy].e0 + kRowCost) > share) ++n_heavy;
+    if (n_heavy) {
+      std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> heap;
+      for (int g = 0; g < G; ++g) heap.push({0, g});
+      for (size_t i = 0; i < n_heavy; ++i) {
+        auto top = heap.top(); heap.pop();
+        bins[top.second].push_back(static_cast<int>(i));
+        load[top.second] = top.first + (items[i].e1 - items[i].e0) + kRowCost;
+        heap.push({load[top.second], top.second});
+      }
+    }
+    long long light = 0;
+    for (size_t i = n_heavy; i < items.size(); ++i) light += items[i].e1 - items[i].e0 + kRowCost;
+    double level = 0.0;                                   // T*
+    {
+      std::vector<long long> sorted_load(load);
+      std::sort(sorted_load.begin(), sorted_load.end());
+      long long below = 0;                                // sum of the j smallest heavy loads
+      for (int j = 1; j <= G; ++j) {
+        below += sorted_load[j - 1];
+        level = static_cast<double>(light + below) / j;   // level if exactly the j lightest bins are topped up
+        if (j == G || level <= static_cast<double>(sorted_load[j])) break;
+      }
+    }
+    {
+      size_t i = n_heavy;
+      double cum_need = 0.0; long long cum_given = 0;
+      for (int g = 0; g < G && i < items.size(); ++g) {
+        cum_need += std::max(0.0, level - static_cast<double>(load[g]));
+        const bool last = g == G - 1;
+        while (i < items.size()) {
+          const long long c = items[i].e1 - items[i].e0 + kRowCost;
+          if (!last && static_cast<double>(cum_given) + 0.5 * static_cast<double>(c) > cum_need) break;
+          bins[g].push_back(static_cast<int>(i)); cum_given += c; ++i;
+        }
+      }
     }
     for (int g = 0; g < G; ++g) {   // the group's segments and entries, contiguous: the CTA stages them in shared memory
       const int seg0 = static_cast<int>(seg.size());
@@ -594,7 +651,12 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users);
       // in top-k mode the slice is masked and selected right away, and its rows of the result go to the caller's buffers on the copy
       // stream while the next slice computes
-      static const int tail_sub = getenv("MRSCORE_TAIL_SUB") ? std::max(8, atoi(getenv("MRSCORE_TAIL_SUB"))) : kTailSubBatch;
+      // (kTailSubBatch users of whole rows = ~1.8 GB of a panel; the rows of a song partition are shorter, so a slice holds more of them
+      // — fewer, larger launches of the tail / mask / select kernels)
+      static const int tail_sub_env = getenv("MRSCORE_TAIL_SUB") ? std::max(8, atoi(getenv("MRSCORE_TAIL_SUB"))) : 0;
+      const long long sub_fit = static_cast<long long>(kTailSubBatch) * round_up(h->S, 32) / h->spitch / (2 * h->num_sms) * (2 * h->num_sms);
+      const int tail_sub = tail_sub_env ? tail_sub_env : static_cast<int>(std::max<long long>(kTailSubBatch, std::min<long long>(sub_fit, 1 << 20)));
+      const int tail_lanes = 2LL * h->n_cols >= h->S ? 32 : (4LL * h->n_cols >= h->S ? 16 : 8);
       const bool sel_needed = model == MODEL_AGG || model == MODEL_STOCH;
       const TopkHostOut* ho = mode == RUN_TOPK ? static_cast<const TopkHostOut*>(host_out) : nullptr;
       for (int s0 = 0; s0 < nb; s0 += tail_sub) {
@@ -603,7 +665,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           PhaseTimer t(h, MR_T_TAIL_SCATTER);
           const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
           MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                           h->d_tr_end, h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], h->stream));
+                                           h->d_tr_end, h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], tail_lanes, h->stream));
         }
         if (mode != RUN_TOPK) continue;
         PhaseTimer t(h, MR_T_TOPK);
@@ -1029,7 +1091,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it — only the
   // tensor engine's user-space IBM path consumes them
   const int n_batches = (U + kUserBatch - 1) / kUserBatch;
-  std::vector<int> rows_all; std::vector<int> grow(static_cast<size_t>(std::max<long long>(nnz, 1)));
+  std::vector<int> rows_all; std::vector<int> grow(h->engine == MR_ENGINE_TENSOR ? static_cast<size_t>(std::max<long long>(nnz, 1)) : 1);
   h->batch_row_off.assign(static_cast<size_t>(n_batches) + 1, 0);
   h->max_batch_rows = 0;
   if (h->engine == MR_ENGINE_TENSOR) {
@@ -1053,7 +1115,7 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     h->d_te_end = d_end;
   }
   if ((rc = slot_upload(h, mr_handle::SL_TE_COL, &h->d_te_col, h->h_te_col.data(), static_cast<size_t>(nnz)))) return rc;
-  if ((rc = slot_upload(h, mr_handle::SL_TE_GROW, &h->d_te_grow, grow.data(), static_cast<size_t>(nnz)))) return rc;
+  if ((rc = slot_upload(h, mr_handle::SL_TE_GROW, &h->d_te_grow, grow.data(), grow.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_RSA, &h->d_rsa, rsa.data(), rsa.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_RSA_F, &h->d_rsa_f, rsaf.data(), rsaf.size()))) return rc;
   if ((rc = slot_upload(h, mr_handle::SL_PAIR_BASE, &h->d_pair_base, pair_base.data(), pair_base.size()))) return rc;
