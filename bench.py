@@ -552,6 +552,8 @@ def main():
             "e2e": {"value": total_pairs * args.steps / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "host_wall_ms_per_call_rank0": e2e_parts},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "checksum": checksum,
+            "topk_select_rows_since_load": {"fast_path_handed_back": info["topk_fast_rejects"], "short_rows_exact_path": info["topk_short_rows"],
+                                            "degenerate_radix": info["topk_degenerate_rows"]},
             "steady_state": {"value": total_pairs * args.steps / (steady_ms_max * 1e-3), "unit": "pairs/s", "ms_per_step": steady_ms_max / args.steps,
                              "what": "the same step without the head-row precompute (head rows of the train set kept across steps)"},
             "precompute_ms_per_step": phases.get("precompute", 0.0) + phases.get("count", 0.0) + phases.get("expand", 0.0) if item_space else 0.0,

@@ -231,7 +231,9 @@ int mr_set_profile(mr_handle* h, int on);                   /* toggle MR_PROFILE
 int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel launches so far, dense operand bytes, n_items, num_sms, device bytes allocated, space, n_head songs,
                                                                  test entries on head songs, test entries on tail songs, head-row exceptions,
                                                                  test users per batch, head_rowsum work groups per batch, users split over groups,
-                                                                 scored columns (= songs of the window), first song of the window] */
+                                                                 scored columns (= songs of the window), first song of the window,
+                                                                 top-k select since mr_load: rows its sampled fast path handed to the exact path, short rows
+                                                                 (exact path by design), degenerate rows (radix select)] */
 void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
 
 #ifdef __cplusplus

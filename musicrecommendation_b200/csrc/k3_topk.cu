@@ -534,6 +534,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
   };
   uint32_t cbin = 0; unsigned long long phi = 0; uint32_t plo = 0; int nd = 0;
   if (!collected) {
+    if (tid == 0 && bp.stats) atomicAdd(bp.stats + (stride > 1 ? 0 : 1), 1u);   // rows the fast path handed back / short rows
     // ---- exact histogram over the whole row
     for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
     if (tid == 0) s_count = 0;
@@ -550,6 +551,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
       cbin = static_cast<uint32_t>(s_ctl[0]);
       int above = s_ctl[1];                 // keys strictly better than everything still undecided
       if (above + s_ctl[2] > kTopkCap) {
+        if (tid == 0 && bp.stats) atomicAdd(bp.stats + 2, 1u);
         // degenerate row: exact radix select of the (need - above) best keys inside bin cbin
         for (;;) {
           __syncthreads();

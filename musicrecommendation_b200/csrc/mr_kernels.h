@@ -115,6 +115,7 @@ struct BlendParams {
   int ubm_int_ok;            // every UBM numerator of the shard is < 2^52: (double)Sint * rsu is strictly monotone in Sint, top-k may compare integers
   const long long* te_end;   // [U] end of each test row's scored columns: te_ptr + 1, or the in-window prefix ends (song window)
   int song_off;              // added to the ranked column ids: first song of the window (0 without one)
+  unsigned int* stats;       // [3] or null: rows the fast path of the select handed to the exact path, short rows (exact path by design), degenerate rows (radix select)
 };
 int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int* te_col, int u0, int n_users, int n_songs,
                        uint64_t* sel, long long sel_pitch_words, cudaStream_t st);

@@ -51,6 +51,7 @@ struct mr_handle {
   // d_tr_end[v] / d_te_end[u]); only the ranked ids handed back are shifted by win_lo again.  Without a window n_cols = S, *_end = *_ptr + 1.
   int win_lo = 0, win_hi = 0, n_cols = 0; bool windowed = false;
   const long long *d_tr_end = nullptr, *d_te_end = nullptr;
+  unsigned int* d_topk_stats = nullptr;   // [3] counters of the top-k select since mr_load (BlendParams::stats)
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
   struct SongInfo { int head; uint32_t v; };   // head row or -1; v = q_26(d_s) of a head song, train listeners of a tail song
@@ -517,10 +518,11 @@ int plan_item_batches_once(mr_handle* h, const std::vector<long long>& hu_ptr, i
       split_rows.push_back(b);
     }
     h->h_split_ptr.push_back(static_cast<int>(split_rows.size()));
-    // Longest-first packing into G bins of equal cost.  Heavy items (more than 1/8 of a bin's share: a percent of the users) go through
-    // the classic LPT heap; the bulk of light items then tops every bin up to the common level T* (sum over bins of max(0, T* - heavy
-    // load) = light cost) in one sequential sweep with cumulative rounding — O(items) instead of a heap operation per user, which at
-    // 110 000 users per shard was half of mr_set_test_users.
+    // Longest-processing-time packing into G bins of equal cost: every item goes to the currently lightest bin.  Costs are small
+    // integers and the minimum load never decreases, so the priority queue is a bucket queue (bins listed by load, a cursor that only
+    // moves up): O(items + largest load) instead of a heap operation per user, which at 110 000 users per shard was half of
+    // mr_set_test_users.  (A plain sequential fill balances the cost model just as well but measured 30 % slower in head_rowsum: LPT
+    // mixes long and short segments in every bin, which averages out what the model gets wrong.)
     {   // counting sort by length, descending, stable
       int max_n = 0;
       for (const Item& it : items) max_n = std::max(max_n, it.e1 - it.e0);
@@ -532,43 +534,18 @@ int plan_item_batches_once(mr_handle* h, const std::vector<long long>& hu_ptr, i
       items.swap(sorted);
     }
     for (auto& v : bins) v.clear();
-    std::vector<long long> load(G, 0);
-    size_t n_heavy = 0;
-    while (n_heavy < items.size() && 8LL * (items[n_heavy].e1 - items[n_heavy].e0 + kRowCost) > share) ++n_heavy;
-    if (n_heavy) {
-      std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> heap;
-      for (int g = 0; g < G; ++g) heap.push({0, g});
-      for (size_t i = 0; i < n_heavy; ++i) {
-        auto top = heap.top(); heap.pop();
-        bins[top.second].push_back(static_cast<int>(i));
-        load[top.second] = top.first + (items[i].e1 - items[i].e0) + kRowCost;
-        heap.push({load[top.second], top.second});
-      }
-    }
-    long long light = 0;
-    for (size_t i = n_heavy; i < items.size(); ++i) light += items[i].e1 - items[i].e0 + kRowCost;
-    double level = 0.0;                                   // T*
     {
-      std::vector<long long> sorted_load(load);
-      std::sort(sorted_load.begin(), sorted_load.end());
-      long long below = 0;                                // sum of the j smallest heavy loads
-      for (int j = 1; j <= G; ++j) {
-        below += sorted_load[j - 1];
-        level = static_cast<double>(light + below) / j;   // level if exactly the j lightest bins are topped up
-        if (j == G || level <= static_cast<double>(sorted_load[j])) break;
-      }
-    }
-    {
-      size_t i = n_heavy;
-      double cum_need = 0.0; long long cum_given = 0;
-      for (int g = 0; g < G && i < items.size(); ++g) {
-        cum_need += std::max(0.0, level - static_cast<double>(load[g]));
-        const bool last = g == G - 1;
-        while (i < items.size()) {
-          const long long c = items[i].e1 - items[i].e0 + kRowCost;
-          if (!last && static_cast<double>(cum_given) + 0.5 * static_cast<double>(c) > cum_need) break;
-          bins[g].push_back(static_cast<int>(i)); cum_given += c; ++i;
-        }
+      std::vector<std::vector<int>> by_load(static_cast<size_t>(2 * (share + cap) + 64));
+      by_load[0].resize(G);
+      for (int g = 0; g < G; ++g) by_load[0][g] = G - 1 - g;      // pop_back hands out bin 0 first
+      size_t cur = 0;
+      for (size_t i = 0; i < items.size(); ++i) {
+        while (by_load[cur].empty()) ++cur;
+        const int g = by_load[cur].back(); by_load[cur].pop_back();
+        bins[g].push_back(static_cast<int>(i));
+        const size_t nl = cur + static_cast<size_t>(items[i].e1 - items[i].e0 + kRowCost);
+        if (nl >= by_load.size()) by_load.resize(nl + nl / 2 + 1);
+        by_load[nl].push_back(g);
       }
     }
     for (int g = 0; g < G; ++g) {   // the group's segments and entries, contiguous: the CTA stages them in shared memory
@@ -786,7 +763,7 @@ int make_blend_params(mr_handle* h, int model, double param, uint64_t seed, long
   bp->model = model;
   bp->ubm_int_ok = h->ubm_int_ok ? 1 : 0;
   bp->rsd_up = h->d_rsd_up;
-  bp->te_end = h->d_te_end; bp->song_off = h->win_lo;
+  bp->te_end = h->d_te_end; bp->song_off = h->win_lo; bp->stats = h->d_topk_stats;
   if (model < MR_UBM || model > MR_STOCH) return fail(h, MR_ERR_BAD_ARG, "unknown model selector %d", model);
   if (model == MR_LC) { bp->alpha = param; bp->one_minus_alpha = 1 - param; }   // rank1 * alpha + rank2 * (1 - alpha), MR:328
   if (model == MR_AGG) {
@@ -938,6 +915,8 @@ int mr_load(mr_handle* h, int n_train, int n_test, int n_songs, const int64_t* t
   std::vector<long long> trp(tr_rowptr, tr_rowptr + T + 1);
   if ((rc = dev_upload(h, &h->d_tr_ptr, trp.data(), trp.size(), h->allocs))) return rc;
   if ((rc = dev_upload(h, &h->d_tr_col, tr_col, static_cast<size_t>(nnz), h->allocs))) return rc;
+  if ((rc = dev_alloc(h, &h->d_topk_stats, 4, h->allocs))) return rc;
+  MR_CUDA(h, cudaMemsetAsync(h->d_topk_stats, 0, 4 * sizeof(unsigned int), h->stream));
   h->d_tr_end = h->d_tr_ptr + 1;
   if (h->windowed) {
     long long* d_end = nullptr;
@@ -1669,10 +1648,12 @@ int mr_reset_timing(mr_handle* h) {
 }
 int mr_get_info(mr_handle* h, int64_t* out, int n) {
   if (!h || !out) return MR_ERR_BAD_ARG;
-  const int64_t v[16] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
+  unsigned int st[4] = {0, 0, 0, 0};
+  if (n > 16 && h->d_topk_stats && cudaMemcpy(st, h->d_topk_stats, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_get_info: reading the select counters failed");
+  const int64_t v[19] = {h->engine, h->launches, static_cast<int64_t>(h->dense_bytes), h->n_items, h->num_sms, static_cast<int64_t>(h->dev_bytes), h->space, h->n_head,
                          h->n_head_entries, h->n_tail_entries, h->n_ex, h->batch_rows, h->n_groups,
-                         h->h_split_ptr.empty() ? 0 : h->h_split_ptr.back(), h->n_cols, h->win_lo};
-  for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
+                         h->h_split_ptr.empty() ? 0 : h->h_split_ptr.back(), h->n_cols, h->win_lo, st[0], st[1], st[2]};
+  for (int i = 0; i < n && i < 19; ++i) out[i] = v[i];
   return MR_OK;
 }
 int mr_prepare(mr_handle* h) {

@@ -450,10 +450,10 @@ class MusicRecommender:
         return dict(zip(_lib.TIMING_NAMES, list(t)))
 
     def info(self) -> dict:
-        v = (C.c_int64 * 16)()
-        self._lib.mr_get_info(self._h, v, 16)
+        v = (C.c_int64 * 19)()
+        self._lib.mr_get_info(self._h, v, 19)
         return dict(zip(["engine", "launches", "dense_bytes", "n_items", "num_sms", "device_bytes", "space", "n_head", "head_entries",
-                         "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users", "n_cols", "win_lo"], list(v)))
+                         "tail_entries", "head_exceptions", "batch_rows", "head_groups", "split_users", "n_cols", "win_lo", "topk_fast_rejects", "topk_short_rows", "topk_degenerate_rows"], list(v)))
 
     # ------------------------------------------------------------------ model file I/O (MR:489-512)
     def writeModelOnFile(self, model: Model, outputFileName: str = "") -> int:
