@@ -191,6 +191,24 @@ __device__ __forceinline__ int prefix_cmp(unsigned long long kb, uint32_t inv, u
   return a < b ? -1 : (a > b ? 1 : 0);
 }
 
+// L2 prefetches.  The select streams a row in dependent rounds (a thread has one or two 32-byte loads in flight, then computes), so a
+// round costs a full DRAM latency.  Short rows (a song partition: a few hundred KB per user) are pulled into L2 whole by a handful of
+// bulk prefetches when the CTA starts — the sampled passes and the collect pass then hit L2, and the row crosses HBM once instead of
+// 1.25-1.5 times; long rows prefetch the lines the collect pass will need kPrefetchRounds rounds ahead.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+constexpr int kPrefetchRounds = 4;
+constexpr int kShortRow = 65536;      // rows up to this many songs are prefetched whole
+
+__device__ __forceinline__ void prefetch_row(const long long* row, int n_songs) {
+  if (!row) return;
+  const long long bytes = static_cast<long long>((n_songs + 31) / 32 * 32) * 8;      // rows are padded to 32 songs
+  for (long long off = static_cast<long long>(threadIdx.x) * 2048; off < bytes; off += static_cast<long long>(kTopkThreads) * 2048)
+    prefetch_l2_bulk(reinterpret_cast<const char*>(row) + off, static_cast<uint32_t>(min(2048LL, bytes - off)));
+}
+
 // Stream the row: f(song, key bits, valid) is called for 4 songs per thread per iteration, the same number of times by every
 // thread of the CTA (so f may use warp collectives); valid is false for listened pairs and past the end of the row.
 // ubm_min: for the pure UBM model the score is monotone in the integer numerator, so the caller may pass the smallest numerator
@@ -253,8 +271,19 @@ template <bool kInt, class F>
 __device__ __forceinline__ void visit_row(const KeyCtx& c, int n_songs, int chunk_stride, F&& f) {
   constexpr int kSteps = kInt ? 2 : 1;                          // steps in flight (the fp64 models already load three arrays per step)
   const int step = 4 * kTopkThreads * chunk_stride;
+  const bool ahead = chunk_stride == 1 && n_songs > kShortRow && (threadIdx.x & 3) == 0;   // one thread per 128-byte line
   for (int base0 = 0; base0 < n_songs; base0 += kSteps * step) {   // the same trip count for every thread: f may use warp collectives
     const int base = base0 + 4 * static_cast<int>(threadIdx.x);
+    if (ahead) {
+#pragma unroll
+      for (int h = 0; h < kSteps; ++h) {
+        const int sp = base + (kPrefetchRounds * kSteps + h) * step;
+        if (sp < n_songs) {
+          if (kInt || c.model != MODEL_IBM) prefetch_l2_line(c.su + sp);
+          if (!kInt && c.model != MODEL_UBM) prefetch_l2_line(c.si + sp);
+        }
+      }
+    }
     long long a[kSteps][4], b[kSteps][4]; double rd[kSteps][4]; uint64_t selw[kSteps];
 #pragma unroll
     for (int h = 0; h < kSteps; ++h) {
@@ -305,11 +334,18 @@ __device__ __forceinline__ unsigned long long proxy_of(const KeyCtx& c, long lon
 // are evaluated exactly.  12 bytes per song instead of 16, no fp64 work per song, and two steps of loads in flight per thread.
 __device__ __forceinline__ void ibm_collect_pass(const KeyCtx& c, const float* __restrict__ rsd_up, int n_songs, unsigned long long thr,
                                                  unsigned long long* s_key, int* s_song, int* s_count) {
-  const int lane = threadIdx.x & 31;
   const float t_f = __double2float_rd(__longlong_as_double(static_cast<long long>(thr)));
   constexpr int kSteps = 2;
   const int step = 4 * kTopkThreads;
+  const bool ahead = n_songs > kShortRow && (threadIdx.x & 3) == 0;
   for (int base0 = 0; base0 < n_songs; base0 += kSteps * step) {
+    if (ahead) {
+#pragma unroll
+      for (int h = 0; h < kSteps; ++h) {
+        const int sp = base0 + (kPrefetchRounds * kSteps + h) * step + 4 * static_cast<int>(threadIdx.x);
+        if (sp < n_songs) prefetch_l2_line(c.si + sp);
+      }
+    }
     long long b[kSteps][4]; float r[kSteps][4];
 #pragma unroll
     for (int h = 0; h < kSteps; ++h) {
@@ -329,24 +365,15 @@ __device__ __forceinline__ void ibm_collect_pass(const KeyCtx& c, const float* _
 #pragma unroll
     for (int h = 0; h < kSteps; ++h) {
       const int s = base0 + h * step + 4 * static_cast<int>(threadIdx.x);
-      bool cand[4]; bool any = false;
+      // songs whose upper bound reaches the threshold are rare (a few per thousand): exact score, and one shared-memory atomic per
+      // surviving song — no ballots or shuffles in the common case
 #pragma unroll
-      for (int t = 0; t < 4; ++t) { cand[t] = b[h][t] > 0 && __fmul_ru(__ll2float_ru(b[h][t]), r[h][t]) >= t_f; any = any || cand[t]; }
-      if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          unsigned long long kb = 0;
-          if (cand[t]) kb = static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(b[h][t]), __ldg(c.rsd + s + t))));
-          const bool ok = cand[t] && kb >= thr;
-          const uint32_t m = __ballot_sync(0xffffffffu, ok);
-          if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(s_count, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (ok) {
-              const int pos = base + __popc(m & ((1u << lane) - 1));
-              if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s + t; }
-            }
+      for (int t = 0; t < 4; ++t) {
+        if (b[h][t] > 0 && __fmul_ru(__ll2float_ru(b[h][t]), r[h][t]) >= t_f) {
+          const unsigned long long kb = static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(b[h][t]), __ldg(c.rsd + s + t))));
+          if (kb >= thr) {
+            const int pos = atomicAdd(s_count, 1);
+            if (pos < kTopkCap) { s_key[pos] = kb; s_song[pos] = s + t; }
           }
         }
       }
@@ -393,7 +420,9 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
   __syncthreads();
   // ---- the cut: highest bin with at least `want` sampled keys in it or above (warp 0); bins >= 2 only, so the threshold is a real proxy value
   if (warp == 0) {
-    const int want = (k + k / 2 + 64 + stride - 1) / stride;
+    // keys aimed at above the cut: k plus a margin for the sampling noise (3 sigma of a 1/stride sample) — 814 for k = 500 with every
+    // 8th chunk sampled, 641 with every 4th (the candidates of a short row then fit 1024 slots and the final sort is half as long)
+    const int want = ((stride >= 8 ? k + k / 2 + 64 : k + k / 4 + 16) + stride - 1) / stride;
     int part = 0;
     for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
     int above_lane = 0;
@@ -425,27 +454,23 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
     __syncthreads();
     return *s_count >= need && *s_count <= kTopkCap;
   }
+  // Candidates are ~2 per thousand songs: a thread that holds some reserves their slots with ONE shared-memory atomic (no ballots or
+  // shuffles in the common no-candidate case; the order inside the buffer is irrelevant, it is sorted afterwards).
   visit_row<kInt>(c, n_songs, 1, [&](int s, const long long* a, const long long* b, const double* rd, uint64_t selw) {
     unsigned long long p[4];
-    bool any = false;
+    int n_ok = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { p[t] = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); any = any || p[t] >= thr; }
-    if (__any_sync(0xffffffffu, any)) {
+    for (int t = 0; t < 4; ++t) { p[t] = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); n_ok += p[t] >= thr ? 1 : 0; }
+    if (n_ok) {
+      int pos = atomicAdd(s_count, n_ok);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const bool ok = p[t] >= thr;
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(s_count, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (ok) {
-            const int pos = base + __popc(m & ((1u << lane) - 1));
-            if (pos < kTopkCap) {
-              s_key[pos] = kInt ? static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(a[t]), c.rsu))) : p[t];
-              s_song[pos] = s + t;
-            }
+        if (p[t] >= thr) {
+          if (pos < kTopkCap) {
+            s_key[pos] = kInt ? static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(a[t]), c.rsu))) : p[t];
+            s_song[pos] = s + t;
           }
+          ++pos;
         }
       }
     }
@@ -478,6 +503,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
   int* o_song = out_song + static_cast<long long>(u) * k;
   double* o_score = out_score + static_cast<long long>(u) * k;
 
+  if (n_songs <= kShortRow) { prefetch_row(c.su, n_songs); prefetch_row(c.si, n_songs); }
   const int stride = n_songs > 65536 ? 8 : (n_songs > 16384 ? 4 : 1);   // rows of a song partition (S / 8 = 48 k songs at MSD scale) sample every 4th chunk
   const int n_valid = n_songs - static_cast<int>(bp.te_end[u] - te_ptr[u]);   // scored pairs of this user (MR:109)
   int need = 0;
