@@ -332,7 +332,8 @@ def main():
         # measured on one B200 (gpurun_out/r02_bench_u13750_md*.json): per 13 750-user batch the step costs 88.7 / 89.7 / 100.3 / 129.7 ms and the
         # precompute 130 / 113 / 57 / 35 ms at min_deg 64 / 150 / 400 / 1000 — few batches per GPU favour a small head
         batches = -(-ds.U // 13750)
-        head_min_deg = 0 if (by_songs or window) else ((400 if batches <= 5 else 150) if msd else 0)
+        # song partitions (gpurun_out/ps_*.json, one GPU emulating 1 of N partitions): 125-150 beats the default 64 by 3-7 % at N = 2, 4, 8
+        head_min_deg = 125 if (by_songs or window) else ((400 if batches <= 5 else 150) if msd else 0)
     t_load0 = time.perf_counter()
     mr = MusicRecommender(ds, device=local_rank, engine=engine, space=space, head_min_deg=head_min_deg, item_batch=args.batch_users, song_window=window)
     lib, h = mr._lib, mr._h

@@ -151,10 +151,10 @@ int launch_select_bits(const BlendParams& bp, const long long* te_ptr, const int
 // One CTA per test user.  Keys are the composite (score bits : 64, ~song : 32), so "larger key" == "better" with ties broken by
 // the smaller song id; scores are >= 0, so their IEEE bit patterns order like unsigned integers.
 // Every bin map below is monotone in the key and only ever a PRE-FILTER; exactness comes from the final sort of the collected keys.
-//   long rows (S > 16384), fast path — 1.25 passes over the row (1.5 below 65 536 songs):
-//     A1  maximum over every 8th chunk of the row (1/8 of it; every 4th chunk for rows of up to 65 536 songs)
+//   long rows (S > 16384), fast path — 1.25 passes over the row:
+//     A1  maximum over every 8th chunk of the row (1/8 of it)
 //     A2  2048-bin logarithmic histogram (64 bins per binade below the maximum) over the same chunks; the bin above which about
-//         (k + k/2) / 8 sampled keys lie gives the cut
+//         1.46 k / 8 sampled keys lie gives the cut
 //     B   ONE full pass collects the keys at or above the cut; accepted when min(k, valid) <= collected <= 2048
 //     For the pure UBM model the score (double)Sint * rsu is strictly monotone in the integer numerator, so A1/A2/B work on the
 //     integers (one 64-bit compare per song in B) and only the collected keys are converted to fp64.  The other models evaluate the
@@ -420,9 +420,9 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
   __syncthreads();
   // ---- the cut: highest bin with at least `want` sampled keys in it or above (warp 0); bins >= 2 only, so the threshold is a real proxy value
   if (warp == 0) {
-    // keys aimed at above the cut: k plus a margin for the sampling noise (3 sigma of a 1/stride sample) — 814 for k = 500 with every
-    // 8th chunk sampled, 641 with every 4th (the candidates of a short row then fit 1024 slots and the final sort is half as long)
-    const int want = ((stride >= 8 ? k + k / 2 + 64 : k + k / 4 + 16) + stride - 1) / stride;
+    // keys aimed at above the cut: k plus 3 sigma of the sampling noise (every 8th chunk: sigma of the full-row count ~ sqrt(8 * want)
+    // ~ 75 for k = 500) — 730 for k = 500, so that the collected keys land in [~520, ~950]: at least k, and the final sort stays at 1024 slots
+    const int want = (k + (46 * k) / 100 + stride - 1) / stride;
     int part = 0;
     for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
     int above_lane = 0;
@@ -504,7 +504,7 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
   double* o_score = out_score + static_cast<long long>(u) * k;
 
   if (n_songs <= kShortRow) { prefetch_row(c.su, n_songs); prefetch_row(c.si, n_songs); }
-  const int stride = n_songs > 65536 ? 8 : (n_songs > 16384 ? 4 : 1);   // rows of a song partition (S / 8 = 48 k songs at MSD scale) sample every 4th chunk
+  const int stride = n_songs > 16384 ? 8 : 1;   // the rows of a song partition (S / 8 = 48 k songs at MSD scale) take the sampled path too
   const int n_valid = n_songs - static_cast<int>(bp.te_end[u] - te_ptr[u]);   // scored pairs of this user (MR:109)
   int need = 0;
   bool collected = false;
