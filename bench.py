@@ -420,9 +420,9 @@ def main():
 
     def step_e2e(verbose=False):
         t = [time.perf_counter()]
-        if item_space:
+        if item_space:      # the build is started on its own stream: the host work of mr_set_test_users below overlaps it, the first mr_topk completes it
             check(lib.mr_invalidate_prepared(h))
-            check(lib.mr_prepare(h))
+            check(lib.mr_prepare_async(h))
         t.append(time.perf_counter())
         check(lib.mr_set_test_users(h, U, p(keep[0][1]), p(keep[1][1]), p(keep[2][1]), 0, 0))
         t.append(time.perf_counter())

@@ -101,6 +101,10 @@ int mr_set_option(mr_handle* h, int option, int64_t value);
 /* Build the item-space head rows (G, Gq of the popular songs) now instead of lazily on the first scoring call
  * that uses them.  One-off per train set: tensor-core GEMMs on the tensor engine, inverted-index scatter otherwise. */
 int mr_prepare(mr_handle* h);
+/* The same build started on a stream of its own: returns as soon as the kernels are queued, so that the caller's next host work
+ * (typically mr_set_test_users of the shard that is about to be scored) overlaps it; the first call that needs the rows completes
+ * the build.  mr_prepare after mr_prepare_async waits for it. */
+int mr_prepare_async(mr_handle* h);
 /* Forget the head rows (their HBM stays allocated): the next mr_prepare / scoring call rebuilds them.  bench.py uses it to put the
  * whole of getUserBasedModel / getItemBasedModel (MR:132-170, 222-261 — they have no amortisable half) inside every timed step. */
 int mr_invalidate_prepared(mr_handle* h);

@@ -18,7 +18,7 @@ MR_OPT_HEAD_MIN_DEG, MR_OPT_ITEM_BATCH, MR_OPT_SONG_WINDOW_LO, MR_OPT_SONG_WINDO
 TIMING_NAMES = ["expand", "count", "agg_ubm", "agg_ibm", "topk", "other", "precompute", "head_rowsum", "tail_scatter"]
 
 # every symbol include/mrscore.h declares
-SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device", "mr_gram_rows_scatter", "mr_peer_alloc", "mr_peer_open", "mr_peer_close",
+SYMBOLS = ["mr_create", "mr_destroy", "mr_last_error", "mr_load", "mr_set_test_users", "mr_prepare", "mr_prepare_async", "mr_counts_ubm", "mr_counts_ibm", "mr_gram_rows_device", "mr_gram_rows_scatter", "mr_peer_alloc", "mr_peer_open", "mr_peer_close",
            "mr_similarity_ubm", "mr_similarity_ibm", "mr_score_dense", "mr_blend_dense", "mr_evaluate_dense", "mr_topk", "mr_topk_device",
            "mr_topk_fetch", "mr_topk_device_ptrs", "mr_set_option", "mr_invalidate_prepared", "mr_score_users", "mr_score_songs", "mr_map_at_k", "mr_write_model", "mr_format_double", "mr_topk_packed", "mr_topk_merge", "mr_gram_rows_scatter_async", "mr_peer_signal", "mr_peer_wait", "mr_sync", "mr_get_timing", "mr_reset_timing", "mr_set_profile", "mr_get_info", "mr_stream",
            "mr_ingest_tsv", "mr_ingest_error", "mr_ingest_dims", "mr_ingest_get", "mr_ingest_free"]
@@ -51,6 +51,7 @@ def load():
     lib.mr_load.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.mr_set_test_users.argtypes = [vp, i32, vp, vp, vp, i64, i64]
     lib.mr_prepare.argtypes = [vp]
+    lib.mr_prepare_async.argtypes = [vp]
     lib.mr_counts_ubm.argtypes = [vp, vp]
     lib.mr_counts_ibm.argtypes = [vp, i32, i32, vp]
     lib.mr_gram_rows_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]

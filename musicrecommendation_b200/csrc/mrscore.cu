@@ -51,6 +51,10 @@ struct mr_handle {
   // d_tr_end[v] / d_te_end[u]); only the ranked ids handed back are shifted by win_lo again.  Without a window n_cols = S, *_end = *_ptr + 1.
   int win_lo = 0, win_hi = 0, n_cols = 0; bool windowed = false;
   const long long *d_tr_end = nullptr, *d_te_end = nullptr;
+  // asynchronous head-row build (mr_prepare_async): the kernels run on pre_stream, ev_pre marks their end; head_pending until the
+  // exception list has been read back and uploaded (finish_head_rows, by the first call that needs the rows)
+  cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre = nullptr; bool head_pending = false; unsigned int* h_n_ex = nullptr;
+  HeadExceptions pend_ex{};
   unsigned int* d_topk_stats = nullptr;   // [3] counters of the top-k select since mr_load (BlendParams::stats)
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
   std::vector<int32_t> deg_song, deg_song_train;
@@ -187,14 +191,14 @@ int check_csr(mr_handle* h, const char* what, int n_rows, int n_cols, const int6
   return MR_OK;
 }
 
-struct PhaseTimer {   // CUDA events on the library stream around one phase (only with MR_PROFILE)
-  mr_handle* h; int phase; bool on;
-  PhaseTimer(mr_handle* hh, int ph) : h(hh), phase(ph), on((hh->flags & MR_PROFILE) != 0) {
-    if (on) cudaEventRecord(h->ev[0], h->stream);
+struct PhaseTimer {   // CUDA events on the library stream (or the given one) around one phase (only with MR_PROFILE)
+  mr_handle* h; int phase; bool on; cudaStream_t st;
+  PhaseTimer(mr_handle* hh, int ph, cudaStream_t s = nullptr) : h(hh), phase(ph), on((hh->flags & MR_PROFILE) != 0), st(s ? s : hh->stream) {
+    if (on) cudaEventRecord(h->ev[0], st);
   }
   ~PhaseTimer() {
     if (!on) return;
-    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventRecord(h->ev[1], st);
     cudaEventSynchronize(h->ev[1]);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->t_ms[phase] += ms;
@@ -302,9 +306,17 @@ int ensure_gram_ws(mr_handle* h, int n_rows) {
 //     6 bytes per entry instead of 8 (zero) + 8 (read) + 6 (write) and has no pack pass: it is what made the sparse 85 % of the head
 //     rows cheap (they carry few events but paid the full dense staging traffic).
 // On the tensor engine (dense-friendly shapes) every row is staged and computed by K1: one 0/1 count GEMM + byte-plane GEMMs of the weights.
-int ensure_head_rows(mr_handle* h) {
-  if (h->head_ready) return MR_OK;
+int finish_head_rows(mr_handle* h);
+
+// Launch the whole build on stream st (the library stream, or pre_stream for mr_prepare_async) and leave the handle in the
+// head_pending state; nothing here waits for the device except the tensor engine's temporary operands.
+int start_head_rows(mr_handle* h, cudaStream_t st) {
+  if (h->head_ready || h->head_pending) return MR_OK;
   int rc;
+  if (st != h->stream) {   // the build overwrites rows that earlier work on the library stream may still be reading
+    MR_CUDA(h, cudaEventRecord(h->ev_pre, h->stream));
+    MR_CUDA(h, cudaStreamWaitEvent(st, h->ev_pre, 0));
+  }
   const bool dbg = getenv("MRSCORE_DEBUG_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -357,27 +369,27 @@ int ensure_head_rows(mr_handle* h) {
     ex.song = reinterpret_cast<int*>(xb + 16 + cap * 12);
     ex.g_extra = reinterpret_cast<uint32_t*>(xb + 16 + cap * 16);
   }
-  auto bail = [&](int code) { cudaStreamSynchronize(h->stream); free_list(tmp); return code; };
-  cudaError_t e = cudaMemsetAsync(ex.count, 0, sizeof(unsigned int), h->stream);
+  auto bail = [&](int code) { cudaStreamSynchronize(st); free_list(tmp); return code; };
+  cudaError_t e = cudaMemsetAsync(ex.count, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
   uint8_t *a_rows = nullptr, *b_plane = nullptr;
   if (tensor) {
     if ((rc = dev_alloc(h, &a_rows, static_cast<size_t>(chunk) * h->pitchT, tmp)) ||
         (rc = dev_alloc(h, &b_plane, static_cast<size_t>(h->S) * h->pitchT * n_planes, tmp))) { free_list(tmp); return rc; }
     // the GEMM epilogues write only the columns < S: the pad columns of the staging rows must not hold garbage (pack reads the full pitch)
-    e = cudaMemsetAsync(g_stage, 0, stage_entries * sizeof(uint32_t), h->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(gq_stage, 0, stage_entries * sizeof(unsigned long long), h->stream);
+    e = cudaMemsetAsync(g_stage, 0, stage_entries * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gq_stage, 0, stage_entries * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
     // the byte planes of q_24(|I_v|) as weighted B operands (built once, reused by every chunk)
-    PhaseTimer t(h, MR_T_EXPAND);
+    PhaseTimer t(h, MR_T_EXPAND, st);
     for (int plane = 0; plane < n_planes; ++plane) {
       int lrc = launch_expand_rows_weighted(h->d_csc_ptr, h->d_csc_idx, h->d_qv, plane, h->S, h->pitchT,
-                                            b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->stream);
+                                            b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, st);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_expand_rows_weighted failed"));
     }
   }
-  if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[mrscore] precompute: allocations %.1f ms (staged rows %d in chunks of %lld, direct rows %d)\n", ms_since(t_start), n_staged, chunk, h->n_head - n_staged); }
+  if (dbg) { cudaStreamSynchronize(st); fprintf(stderr, "[mrscore] precompute: allocations %.1f ms (staged rows %d in chunks of %lld, direct rows %d)\n", ms_since(t_start), n_staged, chunk, h->n_head - n_staged); }
   auto t_loop = now();
   for (int r0 = 0; r0 < n_staged; r0 += static_cast<int>(chunk)) {
     const int nr = std::min<int>(static_cast<int>(chunk), n_staged - r0);
@@ -385,63 +397,78 @@ int ensure_head_rows(mr_handle* h) {
       // G = A_head · A_trT^T as one 0/1 count GEMM; Gq as byte-plane GEMMs (255 * T < 2^31 keeps each plane exact in int32)
       const int n_pad = static_cast<int>(round_up(nr, 128));
       {
-        PhaseTimer t(h, MR_T_EXPAND);
-        int lrc = launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, h->d_head_song + r0, 0, nr, n_pad, h->pitchT, a_rows, h->stream);
+        PhaseTimer t(h, MR_T_EXPAND, st);
+        int lrc = launch_expand_rows(h->d_csc_ptr, h->d_csc_idx, h->d_head_song + r0, 0, nr, n_pad, h->pitchT, a_rows, st);
         h->launches++;
         if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_expand_rows failed"));
       }
-      PhaseTimer t(h, MR_T_COUNT);
-      int lrc = launch_count_gemm(a_rows, n_pad, h->d_AtrT, h->S, h->pitchT, nr, h->S, EPI_I32, g_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream);
+      PhaseTimer t(h, MR_T_COUNT, st);
+      int lrc = launch_count_gemm(a_rows, n_pad, h->d_AtrT, h->S, h->pitchT, nr, h->S, EPI_I32, g_stage, h->spitch, nullptr, nullptr, h->num_sms, st);
       h->launches++;
       for (int plane = 0; plane < n_planes && !lrc; ++plane) {
         lrc = launch_count_gemm(a_rows, n_pad, b_plane + static_cast<size_t>(plane) * h->S * h->pitchT, h->S, h->pitchT, nr, h->S, EPI_ACC_U64,
-                                gq_stage, h->spitch, nullptr, nullptr, h->num_sms, h->stream, 8 * plane, plane > 0);
+                                gq_stage, h->spitch, nullptr, nullptr, h->num_sms, st, 8 * plane, plane > 0);
         h->launches++;
       }
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_count_gemm failed: rc=%d (%s)", lrc, cudaGetErrorString(cudaGetLastError())));
     } else {
-      PhaseTimer t(h, MR_T_PRECOMPUTE);
+      PhaseTimer t(h, MR_T_PRECOMPUTE, st);
       int lrc = launch_gram_head_scatter(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_end,
-                                         h->d_tr_col, h->d_qv, g_stage, gq_stage, h->spitch, packed ? 1 : 0, h->num_sms, h->stream);
+                                         h->d_tr_col, h->d_qv, g_stage, gq_stage, h->spitch, packed ? 1 : 0, h->num_sms, st);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_scatter failed"));
     }
-    PhaseTimer t(h, MR_T_PRECOMPUTE);
-    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->n_cols, h->d_g16, h->d_gq32, ex, h->num_sms, h->stream);
+    PhaseTimer t(h, MR_T_PRECOMPUTE, st);
+    int lrc = launch_pack_head_rows(g_stage, gq_stage, packed ? 1 : 0, r0, nr, h->spitch, h->n_cols, h->d_g16, h->d_gq32, ex, h->num_sms, st);
     h->launches++;
     if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_pack_head_rows failed"));
   }
-  if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[mrscore] precompute: staged rows %.1f ms\n", ms_since(t_loop)); }
+  if (dbg) { cudaStreamSynchronize(st); fprintf(stderr, "[mrscore] precompute: staged rows %.1f ms\n", ms_since(t_loop)); }
   if (n_staged < h->n_head) {
     // direct rows: an L2-sized chunk of final rows at a time
     long long mb = 48;
     if (const char* ev = getenv("MRSCORE_DIRECT_CHUNK_MB")) mb = std::max(1LL, atoll(ev));
     const long long dchunk = std::max<long long>(1, (mb << 20) / (h->spitch * 6));
-    PhaseTimer t(h, MR_T_PRECOMPUTE);
+    PhaseTimer t(h, MR_T_PRECOMPUTE, st);
     for (int r0 = n_staged; r0 < h->n_head; r0 += static_cast<int>(dchunk)) {
       const int nr = std::min<int>(static_cast<int>(dchunk), h->n_head - r0);
       int lrc = launch_gram_head_direct(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_end,
-                                        h->d_tr_col, h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, h->stream);
+                                        h->d_tr_col, h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, st);
       h->launches++;
       if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_direct failed"));
     }
   }
-  // exception list -> CSR by head row (host sort; it is a few thousand entries on MSD-shaped data)
-  unsigned int n_ex = 0;
-  e = cudaMemcpyAsync(&n_ex, ex.count, sizeof n_ex, cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  // the exception count travels to pinned host memory behind the kernels; finish_head_rows picks it up
+  e = cudaMemcpyAsync(h->h_n_ex, ex.count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev_pre, st);
   if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "head-row precompute: %s", cudaGetErrorString(e)));
-  if (dbg) fprintf(stderr, "[mrscore] precompute: kernels %.1f ms, %u exceptions\n", ms_since(t_loop), n_ex);
-  if (n_ex > ex.capacity) return bail(fail(h, MR_ERR_OOM, "head-row exception list overflowed (%u entries)", n_ex));
+  if (!tmp.empty()) { cudaStreamSynchronize(st); free_list(tmp); }     // tensor engine only: its dense operands are temporary
+  if (dbg) fprintf(stderr, "[mrscore] precompute: launched after %.1f ms\n", ms_since(t_start));
+  h->pend_ex = ex;
+  h->head_pending = true;
+  return MR_OK;
+}
+
+// Complete a started build: wait for its kernels, turn the exception list into a CSR by head row (host sort; it is a few thousand
+// entries on MSD-shaped data) and order the library stream behind the build.
+int finish_head_rows(mr_handle* h) {
+  if (h->head_ready) return MR_OK;
+  if (!h->head_pending) return fail(h, MR_ERR_STATE, "no head-row build in flight");
+  int rc;
+  h->head_pending = false;
+  const HeadExceptions ex = h->pend_ex;
+  cudaError_t e = cudaEventSynchronize(h->ev_pre);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "head-row precompute: %s", cudaGetErrorString(e));
+  const unsigned int n_ex = *h->h_n_ex;
+  if (n_ex > ex.capacity) return fail(h, MR_ERR_OOM, "head-row exception list overflowed (%u entries)", n_ex);
   std::vector<int> xr(n_ex), xs(n_ex); std::vector<uint32_t> xg(n_ex); std::vector<unsigned long long> xq(n_ex);
   if (n_ex) {
     e = cudaMemcpy(xr.data(), ex.row, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(xs.data(), ex.song, n_ex * sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(xg.data(), ex.g_extra, n_ex * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(xq.data(), ex.gq_extra, n_ex * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return bail(fail(h, MR_ERR_CUDA, "head-row exception list: %s", cudaGetErrorString(e)));
+    if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "head-row exception list: %s", cudaGetErrorString(e));
   }
-  free_list(tmp);
   std::vector<unsigned int> order(n_ex);
   for (unsigned int i = 0; i < n_ex; ++i) order[i] = i;
   std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) { return xr[a] != xr[b] ? xr[a] < xr[b] : xs[a] < xs[b]; });
@@ -455,9 +482,15 @@ int ensure_head_rows(mr_handle* h) {
   if ((rc = slot_upload(h, mr_handle::SL_EX_GQ, &h->d_ex_gq, eq.data(), eq.size()))) return rc;
   MR_CUDA(h, cudaStreamSynchronize(h->stream));
   h->n_ex = n_ex;
-  if (dbg) fprintf(stderr, "[mrscore] precompute: total %.1f ms\n", ms_since(t_start));
   h->head_ready = true;
   return MR_OK;
+}
+
+int ensure_head_rows(mr_handle* h) {
+  if (h->head_ready) return MR_OK;
+  int rc = start_head_rows(h, h->stream);
+  if (rc) return rc;
+  return finish_head_rows(h);
 }
 
 // Batch plan of the current test shard.  User space: 128-user batches (UMMA M).  Item space: as many test users per batch as the Sint
@@ -806,6 +839,10 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_slice, cudaEventDisableTiming));
+  MR_CUDA(h, cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
+  MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+  MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_n_ex), sizeof(unsigned int)));
+  *h->h_n_ex = 0;
   MR_CUDA(h, cudaEventCreate(&h->ev[0]));
   MR_CUDA(h, cudaEventCreate(&h->ev[1]));
   return MR_OK;
@@ -816,6 +853,9 @@ void mr_destroy(mr_handle* h) {
   if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->ev_slice) cudaEventDestroy(h->ev_slice);
+  if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
+  if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+  if (h->h_n_ex) cudaFreeHost(h->h_n_ex);
   for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);
   if (h->d_g16) cudaFree(h->d_g16);
   if (h->d_gq32) cudaFree(h->d_gq32);
@@ -1471,6 +1511,7 @@ int mr_invalidate_prepared(mr_handle* h) {
   cudaError_t e = cudaSetDevice(h->device);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "mr_invalidate_prepared: %s", cudaGetErrorString(e));
+  if (h->head_pending) { cudaEventSynchronize(h->ev_pre); h->head_pending = false; }   // a build in flight is abandoned once it has drained
   h->head_ready = false; h->n_ex = 0;
   return MR_OK;
 }
@@ -1656,6 +1697,13 @@ int mr_get_info(mr_handle* h, int64_t* out, int n) {
   for (int i = 0; i < n && i < 19; ++i) out[i] = v[i];
   return MR_OK;
 }
+int mr_prepare_async(mr_handle* h) {
+  if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, MR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return start_head_rows(h, h->pre_stream);
+}
+
 int mr_prepare(mr_handle* h) {
   if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
   cudaError_t e = cudaSetDevice(h->device);

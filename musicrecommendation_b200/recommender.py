@@ -311,6 +311,10 @@ class MusicRecommender:
         """Build the item-space head rows now (one-off per train set) instead of lazily."""
         self._check(self._lib.mr_prepare(self._h))
 
+    def prepare_async(self):
+        """Start the head-row build on its own stream and return; the next scoring call completes it (overlaps set_test_users)."""
+        self._check(self._lib.mr_prepare_async(self._h))
+
     def invalidate_prepared(self):
         """Forget the head rows so that the next prepare() / scoring call rebuilds them (bench.py: the whole model build inside a step)."""
         self._check(self._lib.mr_invalidate_prepared(self._h))

@@ -121,3 +121,26 @@ def test_msd_shape_song_partition(mrlib, oracle_lib):
             if kind != _lib.MR_AGG:
                 rest = [window_topk(oracle_lib, model, a, b, 500) for a, b in ((0, lo), (hi, ds.S))]
                 assert_topk_equal(merge_on_device(mr, [rest[0], got, rest[1]], 500), oracle_lib.topk(model, 500))
+
+
+def test_prepare_async_overlaps_set_test_users(mrlib, oracle_lib):
+    """mr_prepare_async starts the head-row build on its own stream; mr_set_test_users of the next shard runs meanwhile and the first
+    scoring call completes the build — same bits as the synchronous order, also when a rebuild is abandoned half-way."""
+    ds = synth(T=12000, U=1040, S=30000, seed=6)
+    want = {m: oracle_lib.topk(oracle_lib.canon_scores(ds, m), 200) for m in (oracle_lib.UBM, oracle_lib.IBM)}
+    with MusicRecommender(ds, head_min_deg=8, **ITEM) as mr:
+        for _ in range(2):
+            mr.invalidate_prepared()
+            mr.prepare_async()
+            mr.set_test_users(ds)
+            assert_topk_equal(mr.getTopK(_lib.MR_UBM, k=200), want[oracle_lib.UBM])
+            assert_topk_equal(mr.getTopK(_lib.MR_IBM, k=200), want[oracle_lib.IBM])
+        assert mr.info()["head_exceptions"] > 0
+        mr.invalidate_prepared()
+        mr.prepare_async()
+        mr.invalidate_prepared()          # abandons the build in flight
+        mr.prepare_async()
+        mr.prepare()                      # waits for it
+        half = ds.shard_test_users(0, 520)
+        mr.set_test_users(half)
+        assert_topk_equal(mr.getTopK(_lib.MR_IBM, k=200), tuple(a[:520] for a in want[oracle_lib.IBM]))
