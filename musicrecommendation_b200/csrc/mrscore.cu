@@ -1231,6 +1231,7 @@ static int gram_range(mr_handle* h, int s0, int s1, int32_t* out_i32, float* out
   if (rc == MR_ERR_STATE && h && h->loaded) rc = MR_OK;   // Gram rows need only the train replica
   if (rc) return rc;
   MR_CUDA(h, cudaSetDevice(h->device));
+  if (h->windowed) return fail(h, MR_ERR_STATE, "Gram rows are not available on a handle with a song window (its song ids are rotated)");
   if (s0 < 0 || s1 > h->S || s0 > s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
   const int chunk = 1024;
   int* d_ids = nullptr; float* d_f = nullptr;
@@ -1264,6 +1265,7 @@ int mr_gram_rows_device(mr_handle* h, int s0, int s1, int32_t** dev_out, int64_t
   if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
   if (!dev_out || !ld) return fail(h, MR_ERR_BAD_ARG, "null output");
   MR_CUDA(h, cudaSetDevice(h->device));
+  if (h->windowed) return fail(h, MR_ERR_STATE, "Gram rows are not available on a handle with a song window (its song ids are rotated)");
   if (s0 < 0 || s1 > h->S || s0 >= s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
   const int n = s1 - s0;
   int rc = ensure_gram_ws(h, n);
@@ -1351,6 +1353,7 @@ static int gram_rows_scatter_impl(mr_handle* h, int s0, int s1, void* const* slo
   if (!h || !h->loaded) return fail(h, MR_ERR_STATE, "mr_load has not succeeded on this handle");
   if (h->engine != MR_ENGINE_TENSOR) return fail(h, MR_ERR_STATE, "mr_gram_rows_scatter needs the tensor engine (the scatter is the GEMM epilogue)");
   MR_CUDA(h, cudaSetDevice(h->device));
+  if (h->windowed) return fail(h, MR_ERR_STATE, "Gram rows are not available on a handle with a song window (its song ids are rotated)");
   if (s0 < 0 || s1 > h->S || s0 >= s1) return fail(h, MR_ERR_BAD_ARG, "song range [%d,%d) outside [0,%d)", s0, s1, h->S);
   const int n = s1 - s0;
   if (!slot_ptrs || n_owners < 1 || n_owners > 8 || rows_per_owner < 1 || static_cast<long long>(n_owners) * rows_per_owner < n || ld < h->S)

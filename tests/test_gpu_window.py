@@ -100,6 +100,9 @@ def test_song_window_argument_checks(mrlib):
         MusicRecommender(ds, song_window=(0, 1000), engine=_lib.MR_ENGINE_TENSOR)
     with MusicRecommender(ds, song_window=(0, 2000)) as mr:     # the whole range is no window
         assert mr.info()["n_cols"] == 2000
+    with MusicRecommender(ds, song_window=(500, 1500)) as mr:   # Gram-row probes address songs by their global id: refused under a window
+        with pytest.raises(_lib.MrError):
+            mr.counts_ibm(0, 10)
 
 
 def test_msd_shape_song_partition(mrlib, oracle_lib):
