@@ -27,6 +27,7 @@ trait MrScore extends Library {
                   outMap: com.sun.jna.ptr.DoubleByReference, outAp: Array[Double]): Int
   def mr_write_model(path: String, scoresUxS: Array[Double], nUsers: Int, nSongs: Int, userChars: Array[Byte], userOff: Array[Long],
                      songChars: Array[Byte], songOff: Array[Long], append: Int, rowsWritten: LongByReference): Int   // writeModelOnFile MR:489-496
+  def mr_prepare_async(h: Pointer): Int   // head-row build on its own stream; the next scoring call completes it
   def mr_set_option(h: Pointer, option: Int, value: Long): Int   // MR_OPT_SONG_WINDOW_LO = 3 / _HI = 4: one song partition of distributed.scala:459-461 per handle
   // join of the partitions' ranked lists (device pointers; the driver-side collect + ranking of distributed.scala:461, 479)
   def mr_topk_merge(h: Pointer, k: Int, nParts: Int, nUsers: Int, partSong: Array[Pointer], partScore: Array[Pointer], partLen: Array[Pointer],
