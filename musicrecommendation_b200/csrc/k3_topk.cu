@@ -308,8 +308,10 @@ __device__ __forceinline__ void visit_row(const KeyCtx& c, int n_songs, int chun
           }
         }
         if (!kInt && c.model >= MODEL_AGG) selw[h] = c.sel[s >> 6] >> (s & 63);
+        if (s + 4 > n_songs) {   // only the last quad of a row can reach past its end
 #pragma unroll
-        for (int t = 0; t < 4; ++t) if (s + t >= n_songs) { a[h][t] = -1; b[h][t] = -1; }
+          for (int t = 0; t < 4; ++t) if (s + t >= n_songs) { a[h][t] = -1; b[h][t] = -1; }
+        }
       }
     }
 #pragma unroll
@@ -456,25 +458,33 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
   }
   // Candidates are ~2 per thousand songs: a thread that holds some reserves their slots with ONE shared-memory atomic (no ballots or
   // shuffles in the common no-candidate case; the order inside the buffer is irrelevant, it is sorted afterwards).
+  // (the integer path keeps the raw numerators in the buffer and converts the few hundred survivors to fp64 after the pass)
+  const long long thr_int = static_cast<long long>(thr);            // >= 1: a listened pair (-1) or a zero score never passes
   visit_row<kInt>(c, n_songs, 1, [&](int s, const long long* a, const long long* b, const double* rd, uint64_t selw) {
     unsigned long long p[4];
     int n_ok = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { p[t] = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); n_ok += p[t] >= thr ? 1 : 0; }
+    for (int t = 0; t < 4; ++t) {
+      if (kInt) { p[t] = static_cast<unsigned long long>(a[t]); n_ok += a[t] >= thr_int ? 1 : 0; }
+      else { p[t] = proxy_of<kInt>(c, a[t], b[t], rd[t], (selw >> t) & 1ULL); n_ok += p[t] >= thr ? 1 : 0; }
+    }
     if (n_ok) {
       int pos = atomicAdd(s_count, n_ok);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        if (p[t] >= thr) {
-          if (pos < kTopkCap) {
-            s_key[pos] = kInt ? static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(a[t]), c.rsu))) : p[t];
-            s_song[pos] = s + t;
-          }
+        if (kInt ? a[t] >= thr_int : p[t] >= thr) {
+          if (pos < kTopkCap) { s_key[pos] = p[t]; s_song[pos] = s + t; }
           ++pos;
         }
       }
     }
   });
+  if (kInt) {
+    __syncthreads();
+    const int n = min(*s_count, kTopkCap);
+    for (int i = threadIdx.x; i < n; i += kTopkThreads)
+      s_key[i] = static_cast<unsigned long long>(__double_as_longlong(__dmul_rn(__ll2double_rn(static_cast<long long>(s_key[i])), c.rsu)));
+  }
   __syncthreads();
   return *s_count >= need && *s_count <= kTopkCap;
 }
