@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -38,10 +39,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not SO.exists():
-        raise ImportError(f"{SO} is missing: build it with `python -m musicrecommendation_b200.build` (needs nvcc). "
+    so = Path(os.environ.get("MRSCORE_SO", SO))      # developer aid: an alternative build of the same library (kernel tuning experiments)
+    if not so.exists():
+        raise ImportError(f"{so} is missing: build it with `python -m musicrecommendation_b200.build` (needs nvcc). "
                           "There is no CPU fallback for the scoring path.")
-    lib = C.CDLL(str(SO))
+    lib = C.CDLL(str(so))
     vp, i32, i64, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
     lib.mr_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32, C.c_uint]
     lib.mr_destroy.argtypes = [vp]
