@@ -22,6 +22,8 @@
 #include <cstring>
 #include <string>
 #include <queue>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace mr;
@@ -178,16 +180,45 @@ inline double rs_of(int32_t deg, double inv) { return deg <= 0 ? 0.0 : inv / std
 inline float rsf_of(int32_t deg) { return deg <= 0 ? 0.0f : static_cast<float>(1.0 / std::sqrt(static_cast<double>(deg))); }
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
+// f(lo, hi) over disjoint row ranges on a few host threads.  The per-shard host work of mr_set_test_users (CSR validation, id rotation,
+// cosine factors: O(test entries)) sits on the calling thread inside every end-to-end step; a rank of an 8-GPU job shares the host with
+// seven others, hence at most hardware threads / 8 (and at most 8) workers.
+template <class F>
+void parallel_rows(int n, F&& f) {
+  const int hw = static_cast<int>(std::thread::hardware_concurrency());
+  const int t = std::max(1, std::min(8, hw / 8));
+  if (n < 16384 || t == 1) { f(0, n); return; }
+  const int chunk = (n + t - 1) / t;
+  std::vector<std::thread> workers;
+  for (int i = 1; i < t; ++i) workers.emplace_back([&f, i, chunk, n] { f(std::min(n, i * chunk), std::min(n, (i + 1) * chunk)); });
+  f(0, std::min(n, chunk));
+  for (auto& w : workers) w.join();
+}
+
 int check_csr(mr_handle* h, const char* what, int n_rows, int n_cols, const int64_t* ptr, const int32_t* col) {
   if (!ptr || (!col && ptr[n_rows] > 0)) return fail(h, MR_ERR_BAD_ARG, "%s: null CSR arrays", what);
   if (ptr[0] != 0) return fail(h, MR_ERR_BAD_ARG, "%s: rowptr[0] != 0", what);
-  for (int r = 0; r < n_rows; ++r) {
+  for (int r = 0; r < n_rows; ++r)
     if (ptr[r + 1] < ptr[r]) return fail(h, MR_ERR_BAD_ARG, "%s: rowptr not monotone at row %d", what, r);
-    for (int64_t i = ptr[r]; i < ptr[r + 1]; ++i) {
-      if (col[i] < 0 || col[i] >= n_cols) return fail(h, MR_ERR_BAD_ARG, "%s: column id %d out of range at row %d", what, col[i], r);
-      if (i > ptr[r] && col[i] <= col[i - 1]) return fail(h, MR_ERR_BAD_ARG, "%s: row %d not ascending/unique", what, r);
+  // the first offending row (smallest index) is reported, whichever thread finds it
+  struct Bad { int row = -1; int kind = 0; int col = 0; };
+  Bad best; std::mutex mu;
+  parallel_rows(n_rows, [&](int lo, int hi) {
+    Bad b;
+    for (int r = lo; r < hi && b.row < 0; ++r) {
+      for (int64_t i = ptr[r]; i < ptr[r + 1]; ++i) {
+        if (col[i] < 0 || col[i] >= n_cols) { b.row = r; b.kind = 1; b.col = col[i]; break; }
+        if (i > ptr[r] && col[i] <= col[i - 1]) { b.row = r; b.kind = 2; break; }
+      }
     }
-  }
+    if (b.row >= 0) {
+      std::lock_guard<std::mutex> g(mu);
+      if (best.row < 0 || b.row < best.row) best = b;
+    }
+  });
+  const Bad& b = best;
+  if (b.row >= 0 && b.kind == 1) return fail(h, MR_ERR_BAD_ARG, "%s: column id %d out of range at row %d", what, b.col, b.row);
+  if (b.row >= 0) return fail(h, MR_ERR_BAD_ARG, "%s: row %d not ascending/unique", what, b.row);
   return MR_OK;
 }
 
@@ -1080,14 +1111,12 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
   const int U = n_test; const long long nnz = te_rowptr[U];
   h->U = U; h->nnz_te = nnz;
   h->h_te_ptr.assign(te_rowptr, te_rowptr + U + 1);
-  h->h_te_col.assign(te_col, te_col + nnz);
+  if (h->windowed) h->h_te_col.resize(static_cast<size_t>(nnz)); else h->h_te_col.assign(te_col, te_col + nnz);   // a window rewrites every row below
   std::vector<double> rsa(U); std::vector<float> rsaf(U);
   std::vector<long long> pair_base(static_cast<size_t>(U) + 1);
   pair_base[0] = pair_index_base;
-  for (int u = 0; u < U; ++u) {
-    rsa[u] = rs_of(deg_test[u], kQInvUbm); rsaf[u] = rsf_of(deg_test[u]);
-    pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
-  }
+  parallel_rows(U, [&](int lo, int hi) { for (int u = lo; u < hi; ++u) { rsa[u] = rs_of(deg_test[u], kQInvUbm); rsaf[u] = rsf_of(deg_test[u]); } });
+  for (int u = 0; u < U; ++u) pair_base[u + 1] = pair_base[u] + (h->S - (te_rowptr[u + 1] - te_rowptr[u]));   // unlistened songs of u (MR:109)
   h->pair_index_base = pair_index_base;
   h->n_pairs_total = n_pairs_total > 0 ? n_pairs_total : pair_base[U] - pair_index_base;
   std::vector<long long> te_wend;
@@ -1096,15 +1125,19 @@ int mr_set_test_users(mr_handle* h, int n_test, const int64_t* te_rowptr, const 
     // pair_base[u] + (c + win_lo) - (listened songs below win_lo) - (listened songs of the window below c): fold the constants into pair_base
     const int lo = h->win_lo, up = h->S - lo;
     te_wend.resize(U);
-    for (int u = 0; u < U; ++u) {
-      const int32_t* b = te_col + te_rowptr[u]; const int32_t* e = te_col + te_rowptr[u + 1];
-      const int32_t* m = std::lower_bound(b, e, lo);
-      int32_t* o = h->h_te_col.data() + te_rowptr[u];
-      for (const int32_t* p = m; p < e; ++p) *o++ = *p - lo;
-      for (const int32_t* p = b; p < m; ++p) *o++ = *p + up;
-      te_wend[u] = te_rowptr[u] + (std::lower_bound(m, e, h->win_hi) - m);
-      pair_base[u] += lo - (m - b);
-    }
+    int32_t* const rot = h->h_te_col.data();
+    const int win_hi = h->win_hi;
+    parallel_rows(U, [&](int u_lo, int u_hi) {
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int32_t* b = te_col + te_rowptr[u]; const int32_t* e = te_col + te_rowptr[u + 1];
+        const int32_t* m = std::lower_bound(b, e, lo);
+        int32_t* o = rot + te_rowptr[u];
+        for (const int32_t* p = m; p < e; ++p) *o++ = *p - lo;
+        for (const int32_t* p = b; p < m; ++p) *o++ = *p + up;
+        te_wend[u] = te_rowptr[u] + (std::lower_bound(m, e, win_hi) - m);
+        pair_base[u] += lo - (m - b);
+      }
+    });
     te_col = h->h_te_col.data();
   }
   // per batch: sorted union of the visible songs (the Gram rows the batch needs) and each entry's row index in it — only the
