@@ -147,3 +147,19 @@ def test_prepare_async_overlaps_set_test_users(mrlib, oracle_lib):
         half = ds.shard_test_users(0, 520)
         mr.set_test_users(half)
         assert_topk_equal(mr.getTopK(_lib.MR_IBM, k=200), tuple(a[:520] for a in want[oracle_lib.IBM]))
+
+
+def test_many_users_take_the_threaded_host_path(mrlib, oracle_lib):
+    """17 000 test users: mr_set_test_users validates and rotates the rows on several host threads (>= 16 384 rows); the second of
+    two song partitions still ranks to the oracle's columns, and a malformed row is still reported by its index."""
+    ds = synth(T=3000, U=17000, S=5000, seed=15)
+    lo, hi = song_window(ds.S, 1, 2)
+    ubm = oracle_lib.canon_scores(ds, oracle_lib.UBM)
+    with MusicRecommender(ds, song_window=(lo, hi), **ITEM) as mr:
+        assert_topk_equal(mr.getTopK(_lib.MR_UBM, k=100), window_topk(oracle_lib, ubm, lo, hi, 100))
+        bad = ds.shard_test_users(0, ds.U)
+        bad.te_col = bad.te_col.copy()
+        e = int(bad.te_ptr[16999])
+        bad.te_col[e + 1] = bad.te_col[e]                    # row 16 999 no longer strictly ascending
+        with pytest.raises(_lib.MrError, match="row 16999 not ascending"):
+            mr.set_test_users(bad)
