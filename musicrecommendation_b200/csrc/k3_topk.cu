@@ -489,6 +489,83 @@ __device__ __forceinline__ bool topk_fast_path(const KeyCtx& c, int n_songs, int
   return *s_count >= need && *s_count <= kTopkCap;
 }
 
+// Trim before the final sort: only the best `need` keys have to be ordered.  The candidates (k plus the sampling margin, ~750 for
+// k = 500) would take a 1024-slot bitonic network although `need` fits 512 slots: a linear histogram of their scores finds the bin of the
+// need-th best, the keys in that bin or above (>= need of them, normally < 512) are compacted to the front, and the network halves (the
+// sort was 1/3 of the kernel's instructions on the 48 k-song rows of a song partition, profiles/r02_topk_partition.md).  Returns the new
+// candidate count (unchanged when the keys are all tied or the chosen bin is too crowded).  A function of its own so that its registers
+// do not weigh on the streaming passes of the kernel.
+__device__ __noinline__ int trim_candidates(unsigned long long* s_key, int* s_song, int* s_hist, unsigned long long* s_max, int* s_ctl,
+                                            int* s_count, int n_cand, int need) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long kv[2]; int sv[2];
+  unsigned long long kmax = 0, kmin = ~0ULL;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = tid + e * kTopkThreads;
+    kv[e] = i < n_cand ? s_key[i] : 0ULL; sv[e] = i < n_cand ? s_song[i] : 0;
+    if (i < n_cand) { kmax = kv[e] > kmax ? kv[e] : kmax; kmin = kv[e] < kmin ? kv[e] : kmin; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmax, o), b = __shfl_xor_sync(0xffffffffu, kmin, o);
+    kmax = a > kmax ? a : kmax; kmin = b < kmin ? b : kmin;
+  }
+  __syncthreads();                                     // every candidate is in registers; the scratch arrays are free
+  if (lane == 0) s_max[warp] = kmax;
+  for (int i = tid; i < kTopkBins; i += kTopkThreads) s_hist[i] = 0;
+  __syncthreads();
+  kmax = 0;
+  for (int i = 0; i < kTopkThreads / 32; ++i) kmax = s_max[i] > kmax ? s_max[i] : kmax;
+  __syncthreads();
+  if (lane == 0) s_max[warp] = kmin;                   // the minimum through a second round on the same scratch array
+  if (tid == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }        // "no bin chosen" reads as kept = 0 below
+  __syncthreads();
+  kmin = ~0ULL;
+  for (int i = 0; i < kTopkThreads / 32; ++i) kmin = s_max[i] < kmin ? s_max[i] : kmin;
+  const double d_lo = __longlong_as_double(static_cast<long long>(kmin)), d_hi = __longlong_as_double(static_cast<long long>(kmax));
+  if (!(d_hi > d_lo)) return n_cand;                   // all candidates tied (uniform across the CTA): nothing to trim by score
+  const double tscale = __ddiv_rn(static_cast<double>(kTopkBins - 1), __dsub_rn(d_hi, d_lo));
+  int tb[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int d = __double2int_rz(__dmul_rn(__dsub_rn(__longlong_as_double(static_cast<long long>(kv[e])), d_lo), tscale));
+    tb[e] = d < 0 ? 0 : (d > kTopkBins - 1 ? kTopkBins - 1 : d);                     // monotone in the key
+    if (tid + e * kTopkThreads < n_cand) atomicAdd(&s_hist[tb[e]], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {                                     // the highest bin with at least `need` keys in it or above
+    int part = 0;
+    for (int i = 0; i < kTopkBins / 32; ++i) part += s_hist[lane * (kTopkBins / 32) + i];
+    int above_lane = 0;
+    for (int l = 0; l < 32; ++l) { const int pp = __shfl_sync(0xffffffffu, part, l); if (l > lane) above_lane += pp; }
+    if (above_lane < need && above_lane + part >= need) {
+      int cum = above_lane, chosen = lane * (kTopkBins / 32);
+      for (int i = kTopkBins / 32 - 1; i >= 0; --i) {
+        const int bin = lane * (kTopkBins / 32) + i;
+        if (cum + s_hist[bin] >= need) { chosen = bin; break; }
+        cum += s_hist[bin];
+      }
+      s_ctl[0] = chosen; s_ctl[1] = cum + s_hist[chosen];
+    }
+  }
+  __syncthreads();
+  const int tbin = s_ctl[0], kept = s_ctl[1];
+  if (kept < need || kept > kTopkThreads) return n_cand;   // (uniform) a crowded bin: keep the whole buffer
+  __syncthreads();
+  if (tid == 0) *s_count = 0;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (tid + e * kTopkThreads < n_cand && tb[e] >= tbin) {
+      const int pos = atomicAdd(s_count, 1);
+      s_key[pos] = kv[e]; s_song[pos] = sv[e];
+    }
+  }
+  __syncthreads();
+  return *s_count;
+}
+
 __global__ void __launch_bounds__(kTopkThreads, 2)
 topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long long* __restrict__ sint_u, const long long* __restrict__ sint_i, long long spitch,
             const uint64_t* __restrict__ sel, long long sel_pitch_words, int u0, int n_songs, const double* __restrict__ rsa,
@@ -645,7 +722,9 @@ topk_kernel(BlendParams bp, const long long* __restrict__ te_ptr, const long lon
     return;
   }
   __syncthreads();
-  const int n_cand = min(s_count, kTopkCap);
+  int n_cand = min(s_count, kTopkCap);
+  if (n_cand > kTopkThreads && n_cand <= 2 * kTopkThreads && need <= kTopkThreads)
+    n_cand = trim_candidates(s_key, s_song, s_hist, s_max, s_ctl, &s_count, n_cand, need);
   int n_sort = 1;
   while (n_sort < n_cand) n_sort <<= 1;
   for (int i = n_cand + tid; i < n_sort; i += kTopkThreads) { s_key[i] = 0; s_song[i] = 0x7fffffff; }   // sorts last
