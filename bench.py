@@ -4,8 +4,10 @@
   python bench.py --gpus N --steps K --warmup W [--workload msd|c1|c2|c3|ksplit] [--impl reference]
 
 Workload `msd` (default) is BASELINE.json configs[3], the whole job: the MSD-shaped synthetic data set (909 318 train users, 384 546
-songs, ~42 M train triplets) and ALL 110 000 test users, sharded by test user over the N GPUs (distributed.scala:450-452), train
-replica on every GPU.  STRONG scaling: the work is fixed, N GPUs split it.  One step = what getUserBasedModel + getItemBasedModel
+songs, ~42 M train triplets) and ALL 110 000 test users on N GPUs.  STRONG scaling: the work is fixed, N GPUs split it — by default
+(N > 1) by SONG: every GPU scores all test users against its 1/N of the songs (the reference's second partitioning,
+distributed.scala:459-461), the ranked lists are exchanged with one NCCL all-to-all per array and joined exactly (mr_topk_merge), so the
+head-row precompute is divided by N instead of replicated; `--partition users` shards the test users instead (distributed.scala:450-452).  One step = what getUserBasedModel + getItemBasedModel
 (+ the new top-500) do for the whole test set, with nothing amortised across steps:
 
     head-row precompute (the only place the item-item intersection counts |U_i ∩ U_j| are computed at this scale; the reference's
@@ -14,8 +16,9 @@ replica on every GPU.  STRONG scaling: the work is fixed, N GPUs split it.  One 
 
 One JSON line on rank 0:
   value         whole-job pairs/s, test CSR already resident in HBM, CUDA events on the library stream, max over ranks
-  e2e           the same through the host-buffer C-ABI: mr_set_test_users (pinned host -> device) + mr_topk (device -> host) and, for N > 1,
-                the NCCL gather of the packed top-k blocks to rank 0 (the reference's `.collect`, DIST:451)
+  e2e           the same through the host-buffer C-ABI: mr_prepare_async + mr_set_test_users (pinned host -> device) + scoring + the lists
+                of this rank's users copied device -> host and, for N > 1, the NCCL gather of the packed top-k blocks to rank 0 (the
+                reference's `.collect`, DIST:451, 461)
   steady_state  the per-step figure WITHOUT the precompute (a service that keeps the train set's head rows): secondary
   roofline      dominant kernel (by CUDA-event share): algorithmic bytes per launch / average launch time vs the measured HBM peak
   cpu_baseline  the oracle's canonical CPU port (OpenMP, all host threads) on a bounded sample of the same test users
