@@ -41,6 +41,10 @@ struct mr_handle {
   int device = 0; int num_sms = 148; unsigned flags = 0; int engine = MR_ENGINE_AUTO;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_slice = nullptr;   // mr_topk streams finished slices of the result to the host beside the compute
+  // Batch pipeline of the item-space top-k (run_batches): the head pass of batch b + 1 is issued on `stream` while the tail scatter, mask
+  // and select of batch b run on slice_stream (higher priority); the two batches use the two Sint panels (a pure model needs only one).
+  // ev_head[p] / ev_done[p]: head pass / slices of the batch in panel p.
+  cudaStream_t slice_stream = nullptr; cudaEvent_t ev_head[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   std::string err;
   long long launches = 0; size_t dev_bytes = 0;
   std::vector<void*> allocs;          // everything freed in mr_destroy
@@ -666,28 +670,49 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
   const bool item_space = h->space == MR_SPACE_ITEM && (mode == RUN_TOPK || mode == RUN_DENSE);
   if (item_space) { int rc = ensure_head_rows(h); if (rc) return rc; }
   const int batch = item_space ? h->batch_rows : kUserBatch;
+  // Batch pipeline (item-space top-k of a pure model over >= 2 batches; not under MR_PROFILE, whose phase timers serialise the
+  // stream): the head pass of batch b + 1 is issued on the library stream while the tail scatter, mask and select of batch b run on
+  // slice_stream.  A pure model leaves the other model's Sint panel idle, so consecutive batches alternate between the two panels: no
+  // extra memory.  Head passes stay in order on h->stream, slices in order on slice_stream; ev_head[p] releases the slices of the batch
+  // in panel p, ev_done[p] releases panel p for the head pass two batches later; the last batch joins slice_stream back into h->stream.
+  // What it buys is the kernel boundaries (the next kernel's CTAs start while the previous grid drains): 727 -> 701 ms for the two
+  // models of the one-GPU job.  Making the kernels truly share the SMs was measured and is WORSE (profiles/r02_summary.md §8): the head
+  // pass lives on every resident CTA working on the same song tile out of L2, and a select streaming 48 GB through L2 beside it breaks that.
+  const bool pipelined = item_space && mode == RUN_TOPK && (model == MODEL_UBM || model == MODEL_IBM) && !(h->flags & MR_PROFILE) &&
+                         h->U > batch && !getenv("MRSCORE_NO_PIPELINE");
+  cudaStream_t const hs = h->stream, ts = pipelined ? h->slice_stream : h->stream;
   for (int b0 = 0; b0 < h->U; b0 += batch) {
     const int nb = std::min(batch, h->U - b0);
     if (item_space) {
       const int models = (need_ubm ? 1 : 0) | (need_ibm ? 2 : 0);
+      const int par = pipelined ? ((b0 / batch) & 1) ^ (model == MODEL_IBM ? 1 : 0) : 0;   // panel of this batch: 0 = d_sint_u, 1 = d_sint_i
+      // the panels of this batch by role (pipelined: the pure model's panel alternates between the two allocations)
+      long long* const panel = par ? h->d_sint_i : h->d_sint_u;
+      long long* const pu = pipelined ? (model == MODEL_UBM ? panel : nullptr) : h->d_sint_u;
+      long long* const pi = pipelined ? (model == MODEL_IBM ? panel : nullptr) : h->d_sint_i;
       {
         PhaseTimer t(h, MR_T_HEAD_ROWSUM);
         const int bi = b0 / batch;
         const int4* grp = h->d_grp_hdr + static_cast<long long>(bi) * h->n_groups;
         const int sp0 = h->h_split_ptr[bi], n_split = h->h_split_ptr[bi + 1] - sp0;
+        if (pipelined && b0 >= 2 * batch) MR_CUDA(h, cudaStreamWaitEvent(hs, h->ev_done[par], 0));   // the slices of two batches ago have left this panel
         if (need_ubm) {
-          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_u, h->spitch, h->stream));
+          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, pu, h->spitch, hs));
           MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
-                                          h->spitch, h->n_cols, h->d_sint_u, h->spitch, h->stream));
+                                          h->spitch, h->n_cols, pu, h->spitch, hs));
         }
         if (need_ibm) {
-          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, h->d_sint_i, h->spitch, h->stream));
+          if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, pi, h->spitch, hs));
           MR_LAUNCH(h, launch_head_rowsum(2, h->head_words_i, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
-                                          h->spitch, h->n_cols, h->d_sint_i, h->spitch, h->stream));
+                                          h->spitch, h->n_cols, pi, h->spitch, hs));
         }
         if (h->n_ex > 0)
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
-                                         h->d_ex_gq, h->d_sint_u, h->d_sint_i, h->spitch, h->stream));
+                                         h->d_ex_gq, pu, pi, h->spitch, hs));
+        if (pipelined) {
+          MR_CUDA(h, cudaEventRecord(h->ev_head[par], hs));
+          MR_CUDA(h, cudaStreamWaitEvent(ts, h->ev_head[par], 0));
+        }
       }
       // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users);
       // in top-k mode the slice is masked and selected right away, and its rows of the result go to the caller's buffers on the copy
@@ -706,25 +731,32 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           PhaseTimer t(h, MR_T_TAIL_SCATTER);
           const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
           MR_LAUNCH(h, launch_tail_scatter(models, h->d_tu_user, h->d_tu_song, h->d_tu_lptr, e0, e1, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr,
-                                           h->d_tr_end, h->d_tr_col, h->d_qv, h->d_qd, b0, h->d_sint_u, h->d_sint_i, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], tail_lanes, h->stream));
+                                           h->d_tr_end, h->d_tr_col, h->d_qv, h->d_qd, b0, pu, pi, h->spitch, h->h_tu_lptr[e1] - h->h_tu_lptr[e0], tail_lanes, ts));
         }
         if (mode != RUN_TOPK) continue;
         PhaseTimer t(h, MR_T_TOPK);
-        long long* su = need_ubm ? h->d_sint_u + static_cast<long long>(s0) * h->spitch : nullptr;
-        long long* si = need_ibm ? h->d_sint_i + static_cast<long long>(s0) * h->spitch : nullptr;
+        long long* su = need_ubm ? pu + static_cast<long long>(s0) * h->spitch : nullptr;
+        long long* si = need_ibm ? pi + static_cast<long long>(s0) * h->spitch : nullptr;
         uint64_t* sel = sel_needed ? h->d_sel + static_cast<long long>(s0) * h->sel_pitch : nullptr;
         const int u0 = b0 + s0;
-        MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_end, h->d_te_col, u0, sn, su, si, h->spitch, h->stream));
-        if (sel_needed) MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, u0, sn, h->n_cols, sel, h->sel_pitch, h->stream));
+        MR_LAUNCH(h, launch_mask_listened(h->d_te_ptr, h->d_te_end, h->d_te_col, u0, sn, su, si, h->spitch, ts));
+        if (sel_needed) MR_LAUNCH(h, launch_select_bits(bp, h->d_te_ptr, h->d_te_col, u0, sn, h->n_cols, sel, h->sel_pitch, ts));
         MR_LAUNCH(h, launch_topk(bp, h->d_te_ptr, su, si, h->spitch, sel, h->sel_pitch, u0, sn, h->n_cols, h->d_rsa, h->d_rsd, k, h->d_out_song,
-                                 h->d_out_score, h->d_out_len, h->stream));
+                                 h->d_out_score, h->d_out_len, ts));
         if (ho) {
-          MR_CUDA(h, cudaEventRecord(h->ev_slice, h->stream));
+          MR_CUDA(h, cudaEventRecord(h->ev_slice, ts));
           MR_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_slice, 0));
           const size_t o = static_cast<size_t>(u0) * k, n = static_cast<size_t>(sn) * k;
           MR_CUDA(h, cudaMemcpyAsync(ho->song + o, h->d_out_song + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
           MR_CUDA(h, cudaMemcpyAsync(ho->score + o, h->d_out_score + o, n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
           MR_CUDA(h, cudaMemcpyAsync(ho->len + u0, h->d_out_len + u0, static_cast<size_t>(sn) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+      }
+      if (pipelined) {
+        MR_CUDA(h, cudaEventRecord(h->ev_done[par], ts));
+        if (b0 + batch >= h->U) {   // last batch: the library stream joins the slices of the last two batches
+          MR_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[par], 0));
+          MR_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[par ^ 1], 0));
         }
       }
       if (mode == RUN_TOPK) continue;   // the batch is finished; RUN_DENSE continues below on the whole batch
@@ -872,6 +904,15 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
   MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_slice, cudaEventDisableTiming));
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
   MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    MR_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority; `stream` has the default (lowest)
+    MR_CUDA(h, cudaStreamCreateWithPriority(&h->slice_stream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 2; ++i) {
+      MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_head[i], cudaEventDisableTiming));
+      MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
   MR_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_n_ex), sizeof(unsigned int)));
   *h->h_n_ex = 0;
   MR_CUDA(h, cudaEventCreate(&h->ev[0]));
@@ -886,6 +927,8 @@ void mr_destroy(mr_handle* h) {
   if (h->ev_slice) cudaEventDestroy(h->ev_slice);
   if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
   if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+  if (h->slice_stream) { cudaStreamSynchronize(h->slice_stream); cudaStreamDestroy(h->slice_stream); }
+  for (int i = 0; i < 2; ++i) { if (h->ev_head[i]) cudaEventDestroy(h->ev_head[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
   if (h->h_n_ex) cudaFreeHost(h->h_n_ex);
   for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);
   if (h->d_g16) cudaFree(h->d_g16);

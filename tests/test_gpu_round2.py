@@ -281,3 +281,39 @@ def test_ksplit_two_ranks_under_torchrun(mrlib):
         import json
         line = json.loads(out.stdout.strip().splitlines()[-1])
         assert line["config"]["every_row_equals_oracle"] is True
+
+
+def test_batch_pipeline_equals_the_serial_order(mrlib, oracle_lib, monkeypatch):
+    """Item-space top-k of a pure model over several batches runs as a two-stream pipeline (head pass of batch b + 1 beside the slices of
+    batch b, consecutive batches in alternating Sint panels; run_batches in mrscore.cu).  Device-resident calls back to back, in both
+    orders, with a blend (both panels), a dense probe and a host-buffer call in between: always the oracle's lists, and the same lists as
+    the serial order (MRSCORE_NO_PIPELINE)."""
+    import ctypes as C
+    monkeypatch.setenv("MRSCORE_ITEM_BATCH", "600")
+    ds = synth(T=3000, U=2500, S=20000, seed=31)     # 5 batches of 500 users; rows long enough for the sampled select
+    k = 200
+    ubm, ibm = oracle_lib.canon_scores(ds, oracle_lib.UBM), oracle_lib.canon_scores(ds, oracle_lib.IBM)
+    want = {_lib.MR_UBM: oracle_lib.topk(ubm, k), _lib.MR_IBM: oracle_lib.topk(ibm, k)}
+    want_lc = oracle_lib.topk(oracle_lib.blend_dense(oracle_lib.LC, 0.5, ubm, ibm, 0), k)
+    with MusicRecommender(ds, **ITEM) as mr:
+        assert mr.info()["batch_rows"] == 500
+        lib, h = mr._lib, mr._h
+
+        def device_topk(model):
+            mr._check(lib.mr_topk_device(h, model, 0.0, 0, k))
+            song, score, ln = np.empty((ds.U, k), np.int32), np.empty((ds.U, k), np.float64), np.empty(ds.U, np.int32)
+            mr._check(lib.mr_topk_fetch(h, k, song.ctypes.data_as(C.c_void_p), score.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p)))
+            return song, score, ln
+
+        for order in ((_lib.MR_UBM, _lib.MR_IBM, _lib.MR_IBM, _lib.MR_UBM), (_lib.MR_IBM, _lib.MR_UBM)):
+            for model in order:
+                mr._check(lib.mr_topk_device(h, model, 0.0, 0, k))      # back to back: the next call starts while nothing has been fetched
+            assert_topk_equal(device_topk(order[-1]), want[order[-1]])
+            for model in order:
+                assert_topk_equal(device_topk(model), want[model])
+            assert_topk_equal(mr.getTopK(_lib.MR_LC, k=k, param=0.5), want_lc)          # both panels, serial path
+            assert_bits_equal(mr.getRanks1(_lib.MR_IBM, [3, 1700]), ibm[[3, 1700]])     # dense probe reuses the panels
+            assert_topk_equal(mr.getTopK(_lib.MR_UBM, k=k), want[_lib.MR_UBM])          # host buffers: slices copied out on the copy stream
+        monkeypatch.setenv("MRSCORE_NO_PIPELINE", "1")
+        for model in (_lib.MR_UBM, _lib.MR_IBM):
+            assert_topk_equal(device_topk(model), want[model])
