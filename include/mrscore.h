@@ -238,7 +238,10 @@ int mr_get_info(mr_handle* h, int64_t* out, int n);          /* [engine, kernel 
                                                                  scored columns (= songs of the window), first song of the window,
                                                                  top-k select since mr_load: rows its sampled fast path handed to the exact path, short rows
                                                                  (exact path by design), degenerate rows (radix select)] */
-void* mr_stream(mr_handle* h);                               /* cudaStream_t all work is issued on */
+void* mr_stream(mr_handle* h);                               /* cudaStream_t every call's work is ordered on: what a caller enqueues on it
+                                                                 after a call returns runs behind that call's results (internally the
+                                                                 batches of a top-k call also use a second stream, joined back before
+                                                                 the call returns) */
 
 #ifdef __cplusplus
 }
