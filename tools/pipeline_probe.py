@@ -97,6 +97,7 @@ def oracle_equal(lists, lo=0, hi=None):
 # ---- A: the whole one-GPU job
 # (the head_hi / residency-cap / carve-out / chaining variants of profiles/r02_pipeline_probe_variants.json were measured with the knobs
 #  of the branch wip/pipeline-variants; the shipped library has the plain pipeline and MRSCORE_NO_PIPELINE only)
+#  profiles/r02_slice_streams_probe.json (two slice streams, matched carve-outs) with those of wip/slice-streams
 VARIANTS = (
     ("serial", dict(NO_PIPELINE=1)),
     ("pipelined", dict()),
@@ -108,8 +109,9 @@ with MusicRecommender(ds, device=0, head_min_deg=150) as mr:
     base = None
     for tag, e in VARIANTS:
         env(**e)
-        r = measure(mr, per_model=True)
-        r.update(measure(mr, rebuild=True))
+        r = measure(mr, per_model=tag in ("serial", "pipelined"))
+        if tag in ("serial", "pipelined"):
+            r.update(measure(mr, rebuild=True))
         got = lists_of(mr)
         if base is None:
             base = got
@@ -124,18 +126,16 @@ with MusicRecommender(ds, device=0, head_min_deg=150) as mr:
     del base
 out["A_whole_job"] = sec
 
-# ---- B: one GPU's share of the 8-GPU song-partitioned job
+# ---- B: one GPU's share of the 8-GPU song-partitioned job (all users in one batch)
 if not a.skip_b:
     lo, hi = song_window(full.S, 3, 8)
     sec = {}
     base = None
-    for tag, cap, e in (("one_batch", 0, dict()), ("two_batches_serial", 55000, dict(NO_PIPELINE=1)), ("two_batches_pipelined", 55000, dict()),
-                        ("four_batches_pipelined", 27500, dict())):
-        with MusicRecommender(ds, device=0, head_min_deg=125, song_window=(lo, hi), item_batch=cap) as mr:
-            mr.prepare()
+    with MusicRecommender(ds, device=0, head_min_deg=125, song_window=(lo, hi)) as mr:
+        mr.prepare()
+        for tag, e in (("one_batch", dict()), ("one_batch_again", dict())):
             env(**e)
             r = measure(mr)
-            r.update(measure(mr, rebuild=True))
             r["batch_rows"] = mr.info()["batch_rows"]
             got = lists_of(mr)
             if base is None:
