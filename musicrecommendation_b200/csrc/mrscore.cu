@@ -45,6 +45,7 @@ struct mr_handle {
   // and select of batch b run on slice_stream (higher priority); the two batches use the two Sint panels (a pure model needs only one).
   // ev_head[p] / ev_done[p]: head pass / slices of the batch in panel p.
   cudaStream_t slice_stream = nullptr; cudaEvent_t ev_head[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t slice_stream2 = nullptr; cudaEvent_t ev_join = nullptr;   // single-batch calls alternate their slices between the two slice streams
   std::string err;
   long long launches = 0; size_t dev_bytes = 0;
   std::vector<void*> allocs;          // everything freed in mr_destroy
@@ -680,7 +681,14 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
   // pass lives on every resident CTA working on the same song tile out of L2, and a select streaming 48 GB through L2 beside it breaks that.
   const bool pipelined = item_space && mode == RUN_TOPK && (model == MODEL_UBM || model == MODEL_IBM) && !(h->flags & MR_PROFILE) &&
                          h->U > batch && !getenv("MRSCORE_NO_PIPELINE");
-  cudaStream_t const hs = h->stream, ts = pipelined ? h->slice_stream : h->stream;
+  // Every other item-space top-k (one batch, e.g. a GPU's share of a song-partitioned job, or a blend) puts consecutive slices on two
+  // alternating streams instead: same idea, the boundaries between the slices' kernels (107.6 -> 105.1 ms for both models of a 1/8 song
+  // partition; next to the batch pipeline it adds nothing).  The two streams' kernels have different shared-memory carve-outs and never
+  // share an SM; asking for matched carve-outs makes them do so and is slower (profiles/r02_summary.md §8).
+  const bool alternating = item_space && mode == RUN_TOPK && !pipelined && !(h->flags & MR_PROFILE) && !getenv("MRSCORE_NO_PIPELINE");
+  const bool streamed = pipelined || alternating;   // the slices run off the library stream and are joined back into it
+  cudaStream_t const hs = h->stream;
+  cudaStream_t const sl[2] = {streamed ? h->slice_stream : h->stream, alternating ? h->slice_stream2 : (streamed ? h->slice_stream : h->stream)};
   for (int b0 = 0; b0 < h->U; b0 += batch) {
     const int nb = std::min(batch, h->U - b0);
     if (item_space) {
@@ -695,7 +703,8 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
         const int bi = b0 / batch;
         const int4* grp = h->d_grp_hdr + static_cast<long long>(bi) * h->n_groups;
         const int sp0 = h->h_split_ptr[bi], n_split = h->h_split_ptr[bi + 1] - sp0;
-        if (pipelined && b0 >= 2 * batch) MR_CUDA(h, cudaStreamWaitEvent(hs, h->ev_done[par], 0));   // the slices of two batches ago have left this panel
+        // the slices that last used this panel (two batches ago in the batch pipeline, else the previous batch) have left it
+        if (streamed && b0 >= (pipelined ? 2 : 1) * batch) MR_CUDA(h, cudaStreamWaitEvent(hs, h->ev_done[par], 0));
         if (need_ubm) {
           if (n_split) MR_LAUNCH(h, launch_zero_rows(h->d_split_rows + sp0, n_split, pu, h->spitch, hs));
           MR_LAUNCH(h, launch_head_rowsum(1, h->head_words_u, h->head_threads, grp, h->n_groups, h->d_seg, h->d_ge_row, h->d_ge_q, h->seg_cap, h->ent_cap, h->d_g16, h->d_gq32,
@@ -709,9 +718,10 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
         if (h->n_ex > 0)
           MR_LAUNCH(h, launch_head_fixup(models, h->d_hu_ptr, h->d_hu_row, h->d_hu_song, h->d_hu_q, b0, nb, h->d_ex_ptr, h->d_ex_song, h->d_ex_g,
                                          h->d_ex_gq, pu, pi, h->spitch, hs));
-        if (pipelined) {
+        if (streamed) {
           MR_CUDA(h, cudaEventRecord(h->ev_head[par], hs));
-          MR_CUDA(h, cudaStreamWaitEvent(ts, h->ev_head[par], 0));
+          MR_CUDA(h, cudaStreamWaitEvent(sl[0], h->ev_head[par], 0));
+          if (alternating) MR_CUDA(h, cudaStreamWaitEvent(sl[1], h->ev_head[par], 0));
         }
       }
       // per slice of users so that the atomics of one launch stay within a few GB of the Sint panels (measured optimum: 300-600 users);
@@ -727,6 +737,7 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
       const TopkHostOut* ho = mode == RUN_TOPK ? static_cast<const TopkHostOut*>(host_out) : nullptr;
       for (int s0 = 0; s0 < nb; s0 += tail_sub) {
         const int sn = std::min(tail_sub, nb - s0);
+        cudaStream_t const ts = sl[(s0 / tail_sub) & 1];
         {
           PhaseTimer t(h, MR_T_TAIL_SCATTER);
           const long long e0 = h->h_tu_ptr[b0 + s0], e1 = h->h_tu_ptr[b0 + s0 + sn];
@@ -752,11 +763,15 @@ int run_batches(mr_handle* h, int model, const BlendParams& bp, int k, RunMode m
           MR_CUDA(h, cudaMemcpyAsync(ho->len + u0, h->d_out_len + u0, static_cast<size_t>(sn) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
         }
       }
-      if (pipelined) {
-        MR_CUDA(h, cudaEventRecord(h->ev_done[par], ts));
-        if (b0 + batch >= h->U) {   // last batch: the library stream joins the slices of the last two batches
+      if (streamed) {
+        if (alternating) {   // the batch's slices end on sl[0]
+          MR_CUDA(h, cudaEventRecord(h->ev_join, sl[1]));
+          MR_CUDA(h, cudaStreamWaitEvent(sl[0], h->ev_join, 0));
+        }
+        MR_CUDA(h, cudaEventRecord(h->ev_done[par], sl[0]));
+        if (b0 + batch >= h->U) {   // last batch: the library stream joins the slices (of the last two batches in the batch pipeline)
           MR_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[par], 0));
-          MR_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[par ^ 1], 0));
+          if (pipelined) MR_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[par ^ 1], 0));
         }
       }
       if (mode == RUN_TOPK) continue;   // the batch is finished; RUN_DENSE continues below on the whole batch
@@ -908,6 +923,8 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
     int prio_lo = 0, prio_hi = 0;
     MR_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority; `stream` has the default (lowest)
     MR_CUDA(h, cudaStreamCreateWithPriority(&h->slice_stream, cudaStreamNonBlocking, prio_hi));
+    MR_CUDA(h, cudaStreamCreateWithPriority(&h->slice_stream2, cudaStreamNonBlocking, prio_hi));
+    MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_head[i], cudaEventDisableTiming));
       MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
@@ -928,6 +945,8 @@ void mr_destroy(mr_handle* h) {
   if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
   if (h->ev_pre) cudaEventDestroy(h->ev_pre);
   if (h->slice_stream) { cudaStreamSynchronize(h->slice_stream); cudaStreamDestroy(h->slice_stream); }
+  if (h->slice_stream2) { cudaStreamSynchronize(h->slice_stream2); cudaStreamDestroy(h->slice_stream2); }
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (int i = 0; i < 2; ++i) { if (h->ev_head[i]) cudaEventDestroy(h->ev_head[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
   if (h->h_n_ex) cudaFreeHost(h->h_n_ex);
   for (int i = 0; i < mr_handle::SL_N; ++i) if (h->slot_p[i]) cudaFree(h->slot_p[i]);

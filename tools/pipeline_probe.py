@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--users", type=int, default=110000)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", type=int, default=32)
+ap.add_argument("--skip-a", action="store_true")
 ap.add_argument("--skip-b", action="store_true")
 a = ap.parse_args()
 full = synth_config("c4")
@@ -103,11 +104,12 @@ VARIANTS = (
     ("pipelined", dict()),
 )
 sec = {}
-with MusicRecommender(ds, device=0, head_min_deg=150) as mr:
-    mr.prepare()
-    sec["info"] = {k: mr.info()[k] for k in ("batch_rows", "n_head", "n_cols", "split_users", "device_bytes")}
+with (MusicRecommender(ds, device=0, head_min_deg=150) if not a.skip_a else __import__("contextlib").nullcontext()) as mr:
+    if mr is not None:
+        mr.prepare()
+        sec["info"] = {k: mr.info()[k] for k in ("batch_rows", "n_head", "n_cols", "split_users", "device_bytes")}
     base = None
-    for tag, e in VARIANTS:
+    for tag, e in (VARIANTS if mr is not None else ()):
         env(**e)
         r = measure(mr, per_model=tag in ("serial", "pipelined"))
         if tag in ("serial", "pipelined"):
@@ -133,7 +135,7 @@ if not a.skip_b:
     base = None
     with MusicRecommender(ds, device=0, head_min_deg=125, song_window=(lo, hi)) as mr:
         mr.prepare()
-        for tag, e in (("one_batch", dict()), ("one_batch_again", dict())):
+        for tag, e in (("one_batch_serial", dict(NO_PIPELINE=1)), ("one_batch_alternating_slice_streams", dict()), ("one_batch_serial_again", dict(NO_PIPELINE=1))):
             env(**e)
             r = measure(mr)
             r["batch_rows"] = mr.info()["batch_rows"]
