@@ -33,6 +33,8 @@ namespace {
 constexpr int kSplitLen = 4096;   // listeners per K2 work item
 // largest degrees whose fixed-point cosine factor stays within 1e-5 relative: 0.5 * sqrt(deg) / 2^k <= 1e-5  <=>  deg <= (2e-5 * 2^k)^2
 constexpr int kMaxDegUbm = 112589;      // (2e-5 * 2^24)^2 = 112 589.99
+constexpr int kPreStreams = 2;          // streams of the in-place head-row build (start_head_rows)
+constexpr int kPreExtraStreams = 3;     // at most 1 + 3 (MRSCORE_PRE_STREAMS)
 constexpr int kMaxDegIbm = 1801439;     // (2e-5 * 2^26)^2 = 1 801 439.85
 
 }  // namespace
@@ -61,6 +63,7 @@ struct mr_handle {
   // asynchronous head-row build (mr_prepare_async): the kernels run on pre_stream, ev_pre marks their end; head_pending until the
   // exception list has been read back and uploaded (finish_head_rows, by the first call that needs the rows)
   cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre = nullptr; bool head_pending = false; unsigned int* h_n_ex = nullptr;
+  cudaStream_t pre_extra[kPreExtraStreams] = {}; cudaEvent_t ev_pre_extra[kPreExtraStreams] = {};   // extra streams of the in-place row build (chunks rotate over them)
   HeadExceptions pend_ex{};
   unsigned int* d_topk_stats = nullptr;   // [3] counters of the top-k select since mr_load (BlendParams::stats)
   uint32_t *d_qv = nullptr, *d_qd = nullptr; double* d_rsd = nullptr; float *d_rsv_f = nullptr, *d_rsd_f = nullptr, *d_rsd_up = nullptr;
@@ -466,12 +469,32 @@ int start_head_rows(mr_handle* h, cudaStream_t st) {
     if (const char* ev = getenv("MRSCORE_DIRECT_CHUNK_MB")) mb = std::max(1LL, atoll(ev));
     const long long dchunk = std::max<long long>(1, (mb << 20) / (h->spitch * 6));
     PhaseTimer t(h, MR_T_PRECOMPUTE, st);
-    for (int r0 = n_staged; r0 < h->n_head; r0 += static_cast<int>(dchunk)) {
+    // Several streams (kPreStreams): the chunks are independent (disjoint rows) and each one is three short enqueues (two memsets + a
+    // kernel of ~1.3 waves), so consecutive chunks rotate over `st` and the extra build streams and the next chunk's CTAs start while
+    // the previous grid drains: 113 -> 83 ms for the 32 k rows of the MSD-shaped set with two streams (profiles/r02_summary.md §10).
+    // Not under MR_PROFILE (the phase timer brackets `st` only).
+    int n_streams = kPreStreams;
+    if (const char* ev = getenv("MRSCORE_PRE_STREAMS")) n_streams = std::max(1, std::min(atoi(ev), 1 + kPreExtraStreams));
+    if (h->flags & MR_PROFILE) n_streams = 1;
+    auto sync_extra = [&] { for (int i = 0; i < kPreExtraStreams; ++i) cudaStreamSynchronize(h->pre_extra[i]); };
+    for (int i = 0; i + 1 < n_streams; ++i) {
+      if ((e = cudaEventRecord(h->ev_pre_extra[i], st)) != cudaSuccess || (e = cudaStreamWaitEvent(h->pre_extra[i], h->ev_pre_extra[i], 0)) != cudaSuccess)
+        return bail(fail(h, MR_ERR_CUDA, "head-row precompute: %s", cudaGetErrorString(e)));
+    }
+    int ci = 0;
+    for (int r0 = n_staged; r0 < h->n_head; r0 += static_cast<int>(dchunk), ++ci) {
       const int nr = std::min<int>(static_cast<int>(dchunk), h->n_head - r0);
+      const int si = ci % n_streams;
       int lrc = launch_gram_head_direct(h->d_head_song, h->d_head_lst_ptr, r0, r0 + nr, h->d_csc_ptr, h->d_csc_idx, h->d_tr_ptr, h->d_tr_end,
-                                        h->d_tr_col, h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, st);
+                                        h->d_tr_col, h->d_qv, h->d_g16, h->d_gq32, h->spitch, h->num_sms, si ? h->pre_extra[si - 1] : st);
       h->launches++;
-      if (lrc) return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_direct failed"));
+      if (lrc) { sync_extra(); return bail(fail(h, MR_ERR_CUDA, "launch_gram_head_direct failed")); }
+    }
+    for (int i = 0; i + 1 < n_streams; ++i) {   // `st` joins the extra streams
+      if ((e = cudaEventRecord(h->ev_pre_extra[i], h->pre_extra[i])) != cudaSuccess || (e = cudaStreamWaitEvent(st, h->ev_pre_extra[i], 0)) != cudaSuccess) {
+        sync_extra();
+        return bail(fail(h, MR_ERR_CUDA, "head-row precompute: %s", cudaGetErrorString(e)));
+      }
     }
   }
   // the exception count travels to pinned host memory behind the kernels; finish_head_rows picks it up
@@ -919,6 +942,10 @@ int mr_create(mr_handle** out, const int* device_ids, int n_devices, unsigned fl
   MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_slice, cudaEventDisableTiming));
   MR_CUDA(h, cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
   MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+  for (int i = 0; i < kPreExtraStreams; ++i) {
+    MR_CUDA(h, cudaStreamCreateWithFlags(&h->pre_extra[i], cudaStreamNonBlocking));
+    MR_CUDA(h, cudaEventCreateWithFlags(&h->ev_pre_extra[i], cudaEventDisableTiming));
+  }
   {
     int prio_lo = 0, prio_hi = 0;
     MR_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority; `stream` has the default (lowest)
@@ -944,6 +971,10 @@ void mr_destroy(mr_handle* h) {
   if (h->ev_slice) cudaEventDestroy(h->ev_slice);
   if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
   if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+  for (int i = 0; i < kPreExtraStreams; ++i) {
+    if (h->pre_extra[i]) { cudaStreamSynchronize(h->pre_extra[i]); cudaStreamDestroy(h->pre_extra[i]); }
+    if (h->ev_pre_extra[i]) cudaEventDestroy(h->ev_pre_extra[i]);
+  }
   if (h->slice_stream) { cudaStreamSynchronize(h->slice_stream); cudaStreamDestroy(h->slice_stream); }
   if (h->slice_stream2) { cudaStreamSynchronize(h->slice_stream2); cudaStreamDestroy(h->slice_stream2); }
   if (h->ev_join) cudaEventDestroy(h->ev_join);
