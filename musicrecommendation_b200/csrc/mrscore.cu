@@ -33,7 +33,7 @@ namespace {
 constexpr int kSplitLen = 4096;   // listeners per K2 work item
 // largest degrees whose fixed-point cosine factor stays within 1e-5 relative: 0.5 * sqrt(deg) / 2^k <= 1e-5  <=>  deg <= (2e-5 * 2^k)^2
 constexpr int kMaxDegUbm = 112589;      // (2e-5 * 2^24)^2 = 112 589.99
-constexpr int kPreStreams = 2;          // streams of the in-place head-row build (start_head_rows)
+constexpr int kPreStreams = 4;          // streams of the in-place head-row build (start_head_rows): 113.8 / 82.9 / 75.8 / 73.4 ms with 1 / 2 / 3 / 4
 constexpr int kPreExtraStreams = 3;     // at most 1 + 3 (MRSCORE_PRE_STREAMS)
 constexpr int kMaxDegIbm = 1801439;     // (2e-5 * 2^26)^2 = 1 801 439.85
 
@@ -471,7 +471,7 @@ int start_head_rows(mr_handle* h, cudaStream_t st) {
     PhaseTimer t(h, MR_T_PRECOMPUTE, st);
     // Several streams (kPreStreams): the chunks are independent (disjoint rows) and each one is three short enqueues (two memsets + a
     // kernel of ~1.3 waves), so consecutive chunks rotate over `st` and the extra build streams and the next chunk's CTAs start while
-    // the previous grid drains: 113 -> 83 ms for the 32 k rows of the MSD-shaped set with two streams (profiles/r02_summary.md §10).
+    // the previous grid drains: 113.8 -> 73.4 ms for the 32 k rows of the MSD-shaped set with four streams (profiles/r02_summary.md §10).
     // Not under MR_PROFILE (the phase timer brackets `st` only).
     int n_streams = kPreStreams;
     if (const char* ev = getenv("MRSCORE_PRE_STREAMS")) n_streams = std::max(1, std::min(atoi(ev), 1 + kPreExtraStreams));
