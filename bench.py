@@ -530,7 +530,8 @@ def main():
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "peak_source": peak_src, "ms_per_launch": dom_ms, "launches_per_step": n_launch[dom], "phase_ms_per_step": phases,
                 "phase_note": "phases and ms_per_launch come from a separate MR_PROFILE pass of the same step (CUDA events around every phase, which "
-                              "serialises the stream); the timed step runs the batches as a two-stream pipeline, so it is a little shorter than their sum"}
+                              "serialises the stream, and builds the head rows on one stream); the timed step runs the batches as a two-stream pipeline and the "
+                              "head-row build on four streams (113 -> 73 ms, profiles/r02_summary.md §10), so it is shorter than their sum"}
         if alg.get(dom):
             roof["achieved"] = alg[dom] / (phases[dom] * 1e-3) / 1e9
             roof["frac"] = roof["achieved"] / hbm_peak
