@@ -79,11 +79,14 @@ def test_head_rows_direct_equals_staged(mrlib, oracle_lib, monkeypatch):
     ds = synth(T=6000, U=1100, S=9000, seed=31)
     want = {"ubm": oracle_lib.canon_scores(ds, oracle_lib.UBM), "ibm": oracle_lib.canon_scores(ds, oracle_lib.IBM)}
     wtop = {k: oracle_lib.topk(v, 300) for k, v in want.items()}
-    for stage_all, chunk_mb in ((False, None), (False, "1"), (True, None)):
+    # chunk_mb = "1": ~50 chunks of in-place rows, rotating over the four build streams (default) or all on one (MRSCORE_PRE_STREAMS=1)
+    for stage_all, chunk_mb, streams in ((False, None, None), (False, "1", None), (False, "1", "1"), (True, None, None)):
         if stage_all:
             monkeypatch.setenv("MRSCORE_PRECOMPUTE_STAGE_ALL", "1")
         if chunk_mb:
             monkeypatch.setenv("MRSCORE_DIRECT_CHUNK_MB", chunk_mb)
+        if streams:
+            monkeypatch.setenv("MRSCORE_PRE_STREAMS", streams)
         with MusicRecommender(ds, head_min_deg=2, **ITEM) as mr:
             assert mr.info()["n_head"] > 1000
             for rebuild in (False, True):
@@ -95,6 +98,7 @@ def test_head_rows_direct_equals_staged(mrlib, oracle_lib, monkeypatch):
                 assert_topk_equal(mr.getTopK(_lib.MR_UBM, k=300), wtop["ubm"])
                 assert_topk_equal(mr.getTopK(_lib.MR_IBM, k=300), wtop["ibm"])
         monkeypatch.delenv("MRSCORE_DIRECT_CHUNK_MB", raising=False)
+        monkeypatch.delenv("MRSCORE_PRE_STREAMS", raising=False)
 
 
 def test_head_min_deg_option_changes_nothing_but_the_split(mrlib, oracle_lib):
